@@ -1,0 +1,62 @@
+"""ctypes binding of ``libprismer_sm100.so`` (the C-ABI declared in ``include/prismer_sm100.h``).
+
+There is NO fallback: if the library is missing, or the device is not sm_100, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_float, c_int, c_longlong, c_uint32, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libprismer_sm100.so")
+
+ERRORS = {-1: "bad shape / argument", -2: "misaligned pointer or leading dimension", -3: "unsupported architecture (needs sm_100)",
+          -4: "CUDA runtime error", -5: "CUDA driver entry point (cuTensorMapEncodeTiled) unavailable"}
+
+
+class PrismerError(RuntimeError):
+    pass
+
+
+class GemmArgs(Structure):
+    _fields_ = [
+        ("A", c_void_p), ("B", c_void_p), ("C", c_void_p),
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("lda", c_longlong), ("ldb", c_longlong), ("ldc", c_longlong),
+        ("transA", c_int), ("transB", c_int),
+        ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_longlong),
+        ("aux_out", c_void_p), ("aux_in", c_void_p), ("ldaux", c_longlong),
+        ("act", c_int), ("act_grad", c_int), ("out_fp32", c_int), ("accumulate", c_int),
+        ("alpha", c_float), ("drop_p", c_float), ("seed", c_void_p), ("rng_stream", c_uint32),
+        ("force_bn", c_int), ("max_ctas", c_int),
+    ]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PrismerError(
+                f"{LIB_PATH} not found: build it with `python -m prismer_b200.build` "
+                "(or `__graft_entry__.build()`); prismer_b200 has no CPU / PyTorch fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    L.prismer_abi_version.restype = c_int
+    L.prismer_check_device.restype = c_int
+    L.prismer_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
+    L.prismer_gemm_bf16.restype = c_int
+    from . import _C_decl
+    _C_decl.declare(L)
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise PrismerError(f"libprismer_sm100 {what} failed: {ERRORS.get(rc, rc)} (code {rc})")

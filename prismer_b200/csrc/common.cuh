@@ -1,0 +1,104 @@
+// Shared device helpers: activations, Philox RNG for dropout, vector load/store, reductions.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+#define PRISMER_OK 0
+#define PRISMER_ERR_SHAPE -1
+#define PRISMER_ERR_ALIGN -2
+#define PRISMER_ERR_ARCH -3
+#define PRISMER_ERR_CUDA -4
+#define PRISMER_ERR_DRIVER -5
+
+// activation codes used across the C-ABI
+enum : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_GELU = 2, ACT_SQRELU = 3, ACT_RELU = 4 };
+
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  switch (act) {
+    case ACT_QUICKGELU: return x / (1.0f + __expf(-1.702f * x));          // utils.py:25  x*sigmoid(1.702x)
+    case ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));  // exact erf GELU (roberta.py:164)
+    case ACT_SQRELU: { float r = fmaxf(x, 0.f); return r * r; }            // utils.py:30
+    case ACT_RELU: return fmaxf(x, 0.f);
+    default: return x;
+  }
+}
+// derivative wrt the pre-activation z
+__device__ __forceinline__ float act_bwd(int act, float z) {
+  switch (act) {
+    case ACT_QUICKGELU: { float s = 1.0f / (1.0f + __expf(-1.702f * z)); return s * (1.0f + 1.702f * z * (1.0f - s)); }
+    case ACT_GELU: {
+      float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
+      float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+      return cdf + z * pdf;
+    }
+    case ACT_SQRELU: return z > 0.f ? 2.0f * z : 0.f;
+    case ACT_RELU: return z > 0.f ? 1.0f : 0.f;
+    default: return 1.0f;
+  }
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 (counter based; same mask in fwd/bwd)
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ Philox(uint64_t seed) : k0(static_cast<uint32_t>(seed)), k1(static_cast<uint32_t>(seed >> 32)) {}
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+// keep-decisions for 8 consecutive elements starting at element index 8*g of stream `stream`:
+// bit j of the result = element 8*g+j is KEPT.  thr16 = round(p * 65536).
+__device__ __forceinline__ uint32_t dropout_keep8(const Philox& ph, uint64_t g, uint32_t stream, uint32_t thr16) {
+  uint4 r = ph(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), stream, 0x5052534Du);
+  uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    m |= ((w[j] & 0xFFFFu) >= thr16 ? 1u : 0u) << (2 * j);
+    m |= ((w[j] >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
+  }
+  return m;
+}
+__device__ __forceinline__ bool dropout_keep1(const Philox& ph, uint64_t idx, uint32_t stream, uint32_t thr16) {
+  return (dropout_keep8(ph, idx >> 3, stream, thr16) >> (idx & 7)) & 1u;
+}
+
+// ------------------------------------------------------------------ small utilities
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+
+static inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? PRISMER_OK : PRISMER_ERR_CUDA; }
+#define LAUNCH_CHECK() cuda_status(cudaGetLastError())

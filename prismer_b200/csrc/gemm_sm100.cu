@@ -1,0 +1,398 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue( A[M,K] . B[N,K]^T )
+//
+//   warp 0      : TMA producer (cp.async.bulk.tensor, 128B-swizzled tiles, mbarrier ring)
+//   warp 1      : tcgen05.mma issuer (one elected thread), accumulators double-buffered in TMEM
+//   warps 2..5  : epilogue (tcgen05.ld TMEM->registers, fused bias / activation / dropout / residual, global store)
+//
+// Either operand may be K-major (contraction dim contiguous, i.e. the nn.Linear layout) or MN-major (contraction dim
+// strided), so fprop (x.W^T), dgrad (dy.W) and wgrad (dy^T.x) all run without materialising a transpose.
+// Replaces the cuBLAS GEMMs behind nn.Linear / nn.MultiheadAttention projections / conv-as-GEMM on the reference hot path
+// (SURVEY.md section 2.3 rows K1,K2,K6-K10,K12-K15).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+#include "prismer_sm100.h"
+
+#include <mutex>
+
+namespace {
+
+constexpr int BM = 128;          // UMMA_M (cta_group::1)
+constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int kNumEpiWarps = 4;
+constexpr int kThreads = 32 * (2 + kNumEpiWarps);
+
+template <int BN> struct Cfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32 for BN in {64,128,256})
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  void* C; long long ldc;
+  const float* bias;
+  const bf16* residual; long long ldr;
+  bf16* aux_out; const bf16* aux_in; long long ldaux;
+  int act;          // activation applied to (acc + bias)
+  int act_grad;     // != 0: out = acc * act'(aux_in)   (dgrad through an activation)
+  int out_fp32;     // C is fp32 (else bf16)
+  int accumulate;   // fp32 out only: C += result
+  float alpha;      // result scale (applied to the accumulator first)
+  float drop_p; uint32_t drop_thr16; float drop_scale; const unsigned long long* seed; uint32_t rng_stream;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                 EpiParams ep) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tmem_full = empty_bar + C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], kNumEpiWarps); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<C::kTmemCols>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + C::kABytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+          const int k0 = kb * BK;
+          if constexpr (!A_MN) {
+            ptx::tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0);            // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)                                  // box {64 m, 64 k} per 64-wide MN atom
+              ptx::tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);            // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per UMMA_K inside the 128 B swizzle span.
+            // MN-major: 64-element MN atoms BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO), advance 16 rows.
+            const uint64_t da = A_MN ? ptx::make_smem_desc_sw128(sa + kk * (UMMA_K * 128), BK * 128, 1024)
+                                     : ptx::make_smem_desc_sw128(sa + kk * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + kk * (UMMA_K * 128), BK * 128, 1024)
+                                     : ptx::make_smem_desc_sw128(sb + kk * (UMMA_K * 2), 16, 1024);
+            ptx::umma_f16(tmem_d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          if (kb == num_k - 1) ptx::umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    const bool has_drop = ep.drop_p > 0.f;
+    unsigned long long seed = 0;
+    if (has_drop) seed = *ep.seed;
+    const Philox philox(seed);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, raw);
+        ptx::tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (row_ok && col0 < N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * ep.alpha;
+          const bool full = (col0 + 32 <= N);
+          // ---- bias
+          if (ep.bias) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { v[j] += __ldg(ep.bias + col0 + j); }
+            }
+          }
+          // ---- aux: save pre-activation / multiply by the activation derivative
+          if (ep.aux_out) {
+            bf16* ap = ep.aux_out + static_cast<long long>(row) * ep.ldaux + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(ap + j) = pack8(v + j);
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { ap[j] = __float2bfloat16(v[j]); }
+            }
+          }
+          if (ep.act_grad) {
+            const bf16* ap = ep.aux_in + static_cast<long long>(row) * ep.ldaux + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float z[8]; unpack8(*reinterpret_cast<const bf16x8*>(ap + j), z);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[j + t] *= act_bwd(ep.act_grad, z[t]);
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { v[j] *= act_bwd(ep.act_grad, __bfloat162float(ap[j])); }
+            }
+          } else if (ep.act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_fwd(ep.act, v[j]);
+          }
+          // ---- dropout on the branch output (before the residual add): roberta.py:138,181
+          if (has_drop) {
+            const unsigned long long e0 = static_cast<unsigned long long>(row) * N + col0;  // N % 8 == 0 enforced on host
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t keep = dropout_keep8(philox, (e0 + j) >> 3, ep.rng_stream, ep.drop_thr16);
+#pragma unroll
+              for (int t = 0; t < 8; ++t) v[j + t] = ((keep >> t) & 1u) ? v[j + t] * ep.drop_scale : 0.f;
+            }
+          }
+          // ---- residual
+          if (ep.residual) {
+            const bf16* rp = ep.residual + static_cast<long long>(row) * ep.ldr + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float r[8]; unpack8(*reinterpret_cast<const bf16x8*>(rp + j), r);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[j + t] += r[t];
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { v[j] += __bfloat162float(rp[j]); }
+            }
+          }
+          // ---- store
+          if (ep.out_fp32) {
+            float* cp = reinterpret_cast<float*>(ep.C) + static_cast<long long>(row) * ep.ldc + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (ep.accumulate) { float4 p = *reinterpret_cast<float4*>(cp + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                *reinterpret_cast<float4*>(cp + j) = o;
+              }
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { cp[j] = ep.accumulate ? cp[j] + v[j] : v[j]; }
+            }
+          } else {
+            bf16* cp = reinterpret_cast<bf16*>(ep.C) + static_cast<long long>(row) * ep.ldc + col0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(cp + j) = pack8(v + j);
+            } else {
+              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { cp[j] = __float2bfloat16(v[j]); }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 map over a row-major [rows, cols] matrix with row stride `ld` elements; box = {box_cols, box_rows}.
+int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_cols,
+                int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return PRISMER_ERR_DRIVER;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? PRISMER_OK : PRISMER_ERR_DRIVER;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, int max_ctas,
+           cudaStream_t stream) {
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;  // per-instantiation; benign race (idempotent)
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) return PRISMER_ERR_CUDA;
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int grid = tiles < max_ctas ? tiles : max_ctas;
+  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  return LAUNCH_CHECK();
+}
+
+int pick_bn(int M, int N, int sms) {
+  // minimise (waves x per-tile cost); per-tile cost ~ BN + fixed overhead (pipeline fill + epilogue tail)
+  const int cand[3] = {256, 128, 64};
+  int best = 128; double best_t = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (bn > 64 && N <= bn / 2) continue;
+    const long long tiles = static_cast<long long>((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double t = static_cast<double>(waves) * (bn + 48.0);
+    if (t < best_t) { best_t = t; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+extern "C" int prismer_gemm_bf16(const PrismerGemmArgs* a, cudaStream_t stream) {
+  if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0) return PRISMER_ERR_SHAPE;
+  if ((a->lda % 8) || (a->ldb % 8)) return PRISMER_ERR_ALIGN;
+  if ((reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15) ||
+      (reinterpret_cast<uintptr_t>(a->C) & 15))
+    return PRISMER_ERR_ALIGN;
+  if (a->drop_p > 0.f && ((a->N % 8) || !a->seed)) return PRISMER_ERR_SHAPE;
+  if (a->accumulate && !a->out_fp32) return PRISMER_ERR_SHAPE;
+  // vector paths need 16 B aligned rows; otherwise fall back is per-element inside the kernel only for the N tail,
+  // so require aligned leading dimensions for every row-addressed operand.
+  const int celt = a->out_fp32 ? 4 : 8;
+  if (a->ldc % celt) return PRISMER_ERR_ALIGN;
+  if (a->residual && (a->ldr % 8)) return PRISMER_ERR_ALIGN;
+  if ((a->aux_out || a->aux_in) && (a->ldaux % 8)) return PRISMER_ERR_ALIGN;
+
+  int bn = a->force_bn ? a->force_bn : pick_bn(a->M, a->N, num_sms());
+  if (bn != 64 && bn != 128 && bn != 256) return PRISMER_ERR_SHAPE;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a->transA) rc = make_map_2d(&ta, a->A, a->M, a->K, a->lda, BK, BM);        // A[M,K]
+  else rc = make_map_2d(&ta, a->A, a->K, a->M, a->lda, 64, BK);                    // A^T stored as [K,M]
+  if (rc) return rc;
+  if (!a->transB) rc = make_map_2d(&tb, a->B, a->N, a->K, a->ldb, BK, bn);        // B[N,K]
+  else rc = make_map_2d(&tb, a->B, a->K, a->N, a->ldb, 64, BK);                    // B^T stored as [K,N]
+  if (rc) return rc;
+
+  EpiParams ep;
+  ep.C = a->C; ep.ldc = a->ldc;
+  ep.bias = a->bias;
+  ep.residual = reinterpret_cast<const bf16*>(a->residual); ep.ldr = a->ldr;
+  ep.aux_out = reinterpret_cast<bf16*>(a->aux_out);
+  ep.aux_in = reinterpret_cast<const bf16*>(a->aux_in);
+  ep.ldaux = a->ldaux;
+  ep.act = a->act; ep.act_grad = a->act_grad;
+  ep.out_fp32 = a->out_fp32; ep.accumulate = a->accumulate;
+  ep.alpha = a->alpha;
+  ep.drop_p = a->drop_p;
+  ep.drop_thr16 = static_cast<uint32_t>(a->drop_p * 65536.0f + 0.5f);
+  ep.drop_scale = a->drop_p > 0.f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
+  ep.seed = a->seed; ep.rng_stream = a->rng_stream;
+  if (ep.act_grad && !ep.aux_in) return PRISMER_ERR_SHAPE;
+
+  const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
+#define DISPATCH(BN_)                                                                       \
+  if (!a->transA && !a->transB) return launch<BN_, false, false>(ta, tb, a->M, a->N, a->K, ep, sms, stream); \
+  if (!a->transA && a->transB) return launch<BN_, false, true>(ta, tb, a->M, a->N, a->K, ep, sms, stream);   \
+  if (a->transA && !a->transB) return launch<BN_, true, false>(ta, tb, a->M, a->N, a->K, ep, sms, stream);   \
+  return launch<BN_, true, true>(ta, tb, a->M, a->N, a->K, ep, sms, stream);
+  if (bn == 256) { DISPATCH(256) }
+  if (bn == 128) { DISPATCH(128) }
+  DISPATCH(64)
+#undef DISPATCH
+}
