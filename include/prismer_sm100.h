@@ -86,6 +86,115 @@ int prismer_layernorm_bwd(const void* dy, long long lddy, const void* x, long lo
                           long long lddx, void* dz, long long lddz, float* dgamma, float* dbeta, int rows, int D,
                           float drop_p, const unsigned long long* seed, uint32_t rng_stream, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused multi-head attention (flash style; scores never reach HBM).
+ *   O[b,i,h,:] = sum_j dropout(softmax_j(scale * Q[b,i,h,:].K[b,j,h,:] + mask))[j] * V[b,j,h,:]
+ * Q/K/V/O are addressed as  base + b*bs + row*rs + h*d  (bf16), so packed QKV projections and grouped K/V buffers are
+ * consumed in place.  key_mask: int64 [B,Lk], 1 = attend (the reference's attention_mask) or NULL; causal as
+ * config.is_decoder (roberta.py:310).  lse: fp32 [B,H,Lq] (needed by the backward), delta: fp32 [B,H,Lq] scratch.
+ * Replaces: nn.MultiheadAttention core (vit.py:52-53, resampler.py:30-31) and RobertaSelfAttention.forward
+ * (roberta.py:106-126: scores, mask add + clamp, softmax, dropout, P.V) and their autograd backward.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct PrismerAttnArgs {
+  const void* q; const void* k; const void* v; void* o;
+  long long q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, o_bs, o_rs;
+  float* lse;
+  const void* key_mask;
+  int B, H, Lq, Lk, d;
+  int causal;
+  float scale;
+  float drop_p;
+  const unsigned long long* seed;
+  uint32_t rng_stream;
+  /* backward only */
+  const void* dout; long long do_bs, do_rs;
+  void* dq; long long dq_bs, dq_rs;
+  void* dk; long long dk_bs, dk_rs;
+  void* dv; long long dv_bs, dv_rs;
+  float* delta;
+} PrismerAttnArgs;
+
+int prismer_attention_fwd(const PrismerAttnArgs* args, cudaStream_t stream);
+int prismer_attention_bwd(const PrismerAttnArgs* args, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Elementwise / reduction helpers (HBM-bound).
+ * --------------------------------------------------------------------------------------------------------- */
+/* out[N] (fp32) += column sums of x bf16 [M,N]: bias gradients of every nn.Linear on the path. */
+int prismer_colsum(const void* x, long long ldx, float* out, int M, int N, cudaStream_t stream);
+/* dz = dy * act'(z)  (n elements, n % 8 == 0): backward of the LM-head GELU (roberta.py:423). */
+int prismer_act_bwd(const void* dy, const void* z, void* dz, long long n, int act, cudaStream_t stream);
+/* y = x * keep/(1-p) with the element-indexed Philox mask (embedding dropout, roberta.py:75; same call = its backward). */
+int prismer_dropout(const void* x, void* y, long long n, float p, const unsigned long long* seed, uint32_t rng_stream,
+                    cudaStream_t stream);
+/* fp32 -> bf16 compute copy of the master weights. */
+int prismer_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+/* Fused AdamW over a flat fp32 buffer (torch.optim.AdamW math; train_caption.py:111-112,133): updates p, m, v and the
+ * bf16 compute copy; grad_scale folds the data-parallel 1/world average. */
+int prismer_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream);
+/* Token assembly (vit.py:141-159): dst[b,n,:] = src[b*n_tok+n,:] + pos[n,:] (+ inst_emb[table[instance(b, nearest(n))]]).
+ * inst: int64 [B,1,Hi,Wi] or NULL; table: int32[256] id -> instance_embedding row (host-drawn random.randint, vit.py:145). */
+int prismer_assemble_tokens(const void* src, const void* pos, const void* inst, const int* table, const void* inst_emb,
+                            void* dst, long long dst_bs, long long dst_rs, int B, int n_tok, int D, int gh, int gw, int Hi,
+                            int Wi, cudaStream_t stream);
+int prismer_assemble_tokens_bwd(const void* ddst, long long ddst_bs, long long ddst_rs, void* dsrc, const void* inst,
+                                const int* table, float* dinst_emb, int B, int n_tok, int D, int gh, int gw, int Hi, int Wi,
+                                cudaStream_t stream);
+/* flags[id & 255] = 1 for each id present in an int64 instance map: device half of ``instance.unique()`` (vit.py:144). */
+int prismer_id_presence(const void* ids, long long n, int* flags, cudaStream_t stream);
+/* dpos[n,:] (fp32) += sum_b sum_slots dtok[b*bs + (slot*slot_stride + n)*rs + :]  (shared positional embedding, vit.py:153-158). */
+int prismer_pos_grad(const void* dtok, long long bs, long long rs, int B, int n_tok, int D, int n_slots, int slot_stride,
+                     float* dpos, cudaStream_t stream);
+/* dst[b, r, :] = src[r, :]  (latents broadcast, resampler.py:47) and its gradient  out[r,:] (fp32) += sum_b d[b,r,:]. */
+int prismer_broadcast_rows(const void* src, void* dst, long long dst_bs, long long dst_rs, int B, int n, int D,
+                           cudaStream_t stream);
+int prismer_reduce_batch(const void* d, long long bs, long long rs, int B, int n, int D, float* out, cudaStream_t stream);
+/* strided row copy / accumulate of bf16 rows (torch.cat / gradient joins on the path). */
+int prismer_copy_rows(const void* src, long long lds, void* dst, long long ldd, long long rows, int D, int add,
+                      cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Decoder embeddings (roberta.py:38-45,66-72) and LM loss (roberta.py:381-387; prismer_caption.py:33).
+ * --------------------------------------------------------------------------------------------------------- */
+int prismer_embed_fwd(const void* ids, const void* word, const void* pos, const void* type, void* out, int* pos_ids, int B,
+                      int T, int H, int pad_id, int past_len, cudaStream_t stream);
+int prismer_embed_bwd(const void* de, const void* ids, const int* pos_ids, float* dword, float* dpos, float* dtype, int rows,
+                      int H, int pad_id, cudaStream_t stream);
+/* logits fp32 [B*T, V] (ld); labels int64 [B,T] (unshifted, -100 = ignore); label smoothing; per-sample sums; mean. */
+int prismer_ce_loss_fwd(const float* logits, long long ld, const void* labels, const float* weights, float* row_loss,
+                        float* row_lse, float* sample_loss, float* mean_loss, int B, int T, int V, float smoothing,
+                        cudaStream_t stream);
+int prismer_ce_loss_bwd(const float* logits, long long ld, const void* labels, const float* row_lse, const float* weights,
+                        const float* gscale, void* dlogits, long long ldo, int B, int T, int V, float smoothing,
+                        cudaStream_t stream);
+/* out[r] (int64) = argmax_v logits[r, v] (lowest index on ties, as torch.argmax); eos masked when suppress_eos. */
+int prismer_argmax(const float* logits, long long ld, int rows, int V, int suppress_eos, int eos, void* out,
+                   cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Conv stems (vit.py:86-120) around the GEMM: activations are NHWC bf16, GEMM K order is (kh, kw, c).
+ * --------------------------------------------------------------------------------------------------------- */
+int prismer_patchify(const float* x, void* out, int B, int Cin, int R, int p, int Kpad, cudaStream_t stream);
+int prismer_resample_bilinear(const float* x, void* out, int B, int C, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
+int prismer_im2col_first(const void* in, int in_is_bf16, long long sb, long long sc, long long sy, long long sx, void* out,
+                         int B, int Cin, int H, int W, int ksz, int stride, int Ho, int Wo, int Kpad, cudaStream_t stream);
+int prismer_im2col_nhwc(const void* in, const float* scale, const float* shift, void* out, int B, int H, int W, int C, int ksz,
+                        int stride, int Ho, int Wo, cudaStream_t stream);
+/* BatchNorm2d (eps 1e-5, momentum 0.1): batch statistics in training (running stats updated in place) or running stats in
+ * eval -> per-channel (scale, shift) applied by the consumer's im2col, plus (mean, rstd) for the backward. */
+int prismer_bn_stats(const void* y, float* acc, long long M, int C, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float* scale, float* shift, float* mean, float* rstd, float eps, float momentum,
+                     int training, cudaStream_t stream);
+/* BatchNorm(train) + ReLU backward fused with the consumer conv's col2im: dAcol -> dy (grad wrt the raw conv output). */
+int prismer_bn_relu_bwd(const void* dAcol, const void* y, const float* scale, const float* shift, const float* mean,
+                        const float* rstd, const float* gamma, void* dn_scratch, void* dy, float* red, float* dgamma,
+                        float* dbeta, int B, int H, int W, int C, int ksz, int stride, int Ho, int Wo, cudaStream_t stream);
+int prismer_conv_weight_pack(const float* w, void* out, int Cout, int Cin, int ksz, int Kpad, cudaStream_t stream);
+int prismer_conv_weight_unpack_grad(const float* dwp, float* grad, int Cout, int Cin, int ksz, int Kpad, cudaStream_t stream);
+int prismer_cast_pad(const float* src, void* dst, long long R, int C, int Cpad, cudaStream_t stream);
+int prismer_unpad_add(const float* src, float* dst, long long R, int C, int Cpad, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

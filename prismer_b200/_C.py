@@ -53,6 +53,9 @@ def _declare(L):
     L.prismer_check_device.restype = c_int
     L.prismer_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
     L.prismer_gemm_bf16.restype = c_int
+    for fn in ("prismer_attention_fwd", "prismer_attention_bwd"):
+        getattr(L, fn).argtypes = [POINTER(AttnArgs), c_void_p]
+        getattr(L, fn).restype = c_int
     from . import _C_decl
     _C_decl.declare(L)
 
@@ -60,3 +63,19 @@ def _declare(L):
 def check(rc: int, what: str = ""):
     if rc != 0:
         raise PrismerError(f"libprismer_sm100 {what} failed: {ERRORS.get(rc, rc)} (code {rc})")
+
+
+class AttnArgs(Structure):
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("o", c_void_p),
+        ("q_bs", c_longlong), ("q_rs", c_longlong), ("k_bs", c_longlong), ("k_rs", c_longlong),
+        ("v_bs", c_longlong), ("v_rs", c_longlong), ("o_bs", c_longlong), ("o_rs", c_longlong),
+        ("lse", c_void_p), ("key_mask", c_void_p),
+        ("B", c_int), ("H", c_int), ("Lq", c_int), ("Lk", c_int), ("d", c_int), ("causal", c_int),
+        ("scale", c_float), ("drop_p", c_float), ("seed", c_void_p), ("rng_stream", c_uint32),
+        ("dout", c_void_p), ("do_bs", c_longlong), ("do_rs", c_longlong),
+        ("dq", c_void_p), ("dq_bs", c_longlong), ("dq_rs", c_longlong),
+        ("dk", c_void_p), ("dk_bs", c_longlong), ("dk_rs", c_longlong),
+        ("dv", c_void_p), ("dv_bs", c_longlong), ("dv_rs", c_longlong),
+        ("delta", c_void_p),
+    ]

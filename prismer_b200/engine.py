@@ -1,0 +1,853 @@
+"""Host-side execution engine of the Prismer hot path.
+
+Pure orchestration: every arithmetic step is a call into ``libprismer_sm100.so`` through ``prismer_b200.ops``.  The
+engine owns
+
+* the parameter store: fp32 master weights (the reference-layout ``nn.Parameter`` s become views of one flat buffer),
+  their bf16 compute copies, one flat fp32 gradient buffer (the single all-reduce payload) -- laid out so that the
+  decoder's q/k/v projections and the 12 cross-attention K/V projections are contiguous and run as grouped GEMMs;
+* hand-written forward *and* backward of every block (no autograd graph inside; one ``autograd.Function`` at the top
+  so ``loss.backward()`` keeps working for the reference training loops).
+
+Layouts: encoder activations are seq-first rows ``r = s*B + b`` (the reference's own [S,B,D]); decoder activations are
+batch-first rows ``r = b*T + t``; the decoder reads the encoder output in place through strides.
+"""
+from __future__ import annotations
+
+import math
+import random
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import BF16, F32, gemm
+
+LN_EPS = 1e-5
+
+# dropout call-site ids (Philox streams)
+_RS_EMB, _RS_SELF_P, _RS_SELF_O, _RS_CROSS_P, _RS_CROSS_O, _RS_MLP_O = 1, 2, 3, 4, 5, 6
+
+
+def _site(kind: int, layer: int) -> int:
+    return kind * 64 + layer
+
+
+# ======================================================================================================================
+# parameter store
+# ======================================================================================================================
+class ParamStore:
+    """Flat fp32 master / bf16 compute / fp32 gradient buffers behind the model's ``nn.Parameter`` objects."""
+
+    def __init__(self, root: nn.Module, device: torch.device):
+        from .modules.roberta import RobertaEncoder, RobertaSelfAttention
+        self.root = root
+        self.device = device
+        params: List[nn.Parameter] = []
+        seen = set()
+
+        def add(p):
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+
+        groups = []  # lists of parameters that must be adjacent (same requires_grad)
+        for m in root.modules():
+            if isinstance(m, RobertaEncoder):
+                xs = [layer[1].self for layer in m.layer]
+                groups.append(("xkv_w", m, [p for a in xs for p in (a.key.weight, a.value.weight)]))
+                groups.append(("xkv_b", m, [p for a in xs for p in (a.key.bias, a.value.bias)]))
+        cross = {id(layer[1].self) for m in root.modules() if isinstance(m, RobertaEncoder) for layer in m.layer}
+        for m in root.modules():
+            if isinstance(m, RobertaSelfAttention) and id(m) not in cross:
+                groups.append(("qkv_w", m, [m.query.weight, m.key.weight, m.value.weight]))
+                groups.append(("qkv_b", m, [m.query.bias, m.key.bias, m.value.bias]))
+        for _, _, ps in groups:
+            for p in ps:
+                add(p)
+        for p in root.parameters():
+            add(p)
+        self.params = params
+        self.signature = tuple(p.requires_grad for p in params)
+
+        def layout(ps):
+            off, offs = 0, []
+            for p in ps:
+                offs.append(off)
+                off += (p.numel() + 7) // 8 * 8
+            return offs, off
+
+        self.train_params = [p for p in params if p.requires_grad]
+        self.frozen_params = [p for p in params if not p.requires_grad]
+        t_offs, t_n = layout(self.train_params)
+        f_offs, f_n = layout(self.frozen_params)
+        self.master_t = torch.zeros(max(t_n, 8), dtype=F32, device=device)
+        self.master_f = torch.zeros(max(f_n, 8), dtype=F32, device=device)
+        self.c16_t = torch.zeros(max(t_n, 8), dtype=BF16, device=device)
+        self.c16_f = torch.zeros(max(f_n, 8), dtype=BF16, device=device)
+        self.grad_t = torch.zeros(max(t_n, 8), dtype=F32, device=device)
+        self.n_train = t_n
+        self._offset = {}
+        for ps, offs, master, c16, trainable in ((self.train_params, t_offs, self.master_t, self.c16_t, True),
+                                                 (self.frozen_params, f_offs, self.master_f, self.c16_f, False)):
+            for p, o in zip(ps, offs):
+                n = p.numel()
+                master[o:o + n].copy_(p.data.reshape(-1).to(device=device, dtype=F32))
+                p.data = master[o:o + n].view(p.shape)
+                p._c16 = c16[o:o + n].view(p.shape)
+                p._g32 = self.grad_t[o:o + n].view(p.shape) if trainable else None
+                p.grad = None
+                self._offset[id(p)] = (trainable, o)
+        # grouped views
+        for kind, mod, ps in groups:
+            trainable, o0 = self._offset[id(ps[0])]
+            assert all(self._offset[id(p)][0] == trainable for p in ps), "grouped parameters must share requires_grad"
+            n = sum(p.numel() for p in ps)
+            exp = o0
+            for p in ps:
+                assert self._offset[id(p)][1] == exp and p.numel() % 8 == 0, "grouped parameters are not adjacent"
+                exp += p.numel()
+            master, c16 = (self.master_t, self.c16_t) if trainable else (self.master_f, self.c16_f)
+            ns = getattr(mod, "_grp", None) or SimpleNamespace()
+            if kind.endswith("_w"):
+                cols = ps[0].shape[1]
+                ns.w16 = c16[o0:o0 + n].view(n // cols, cols)
+                ns.wg = self.grad_t[o0:o0 + n].view(n // cols, cols) if trainable else None
+            else:
+                ns.b = master[o0:o0 + n]
+                ns.bg = self.grad_t[o0:o0 + n] if trainable else None
+            mod._grp = ns
+        self._v_t = self._v_f = -1
+        for m in root.modules():
+            m._prismer_store = self
+        self.seed = torch.zeros(1, dtype=torch.int64, device=device)
+        self.refresh(force=True)
+
+    # -- bf16 compute copies ------------------------------------------------------------------------------------------
+    def refresh(self, force: bool = False):
+        """Re-derive the bf16 compute copies when the fp32 masters changed (optimizer step, load_state_dict)."""
+        changed = False
+        if force or self.master_f._version != self._v_f:
+            ops.cast_bf16(self.master_f, self.c16_f)
+            self._v_f = self.master_f._version
+            changed = True
+        if force or self.master_t._version != self._v_t:
+            ops.cast_bf16(self.master_t, self.c16_t)
+            self._v_t = self.master_t._version
+            changed = True
+        if changed:
+            self._repack_convs()
+
+    def mark_fresh(self):
+        """Called by the fused optimizer, which writes the bf16 copies itself."""
+        self._v_t = self.master_t._version
+        self._repack_convs(trainable_only=True)
+
+    def _repack_convs(self, trainable_only: bool = False):
+        for p in self.params:
+            if p.dim() != 4 or (trainable_only and not p.requires_grad):
+                continue
+            cout, cin, k, _ = p.shape
+            K = cin * k * k
+            if k == 3:
+                p._pack16 = ops.conv_weight_pack(p.data, (K + 7) // 8 * 8)
+            elif K % 8 == 0:
+                p._pack16 = p._c16.view(cout, K)   # 1x1 / patch conv: natural flatten == (c, kh, kw) K order
+            else:
+                p._pack16 = ops.cast_pad(p.data.view(cout, K), (K + 7) // 8 * 8)
+
+    def zero_grad(self):
+        self.grad_t.zero_()
+
+    def publish_grads(self):
+        for p in self.train_params:
+            p.grad = p._g32
+
+
+def prepare(root: nn.Module, device=None) -> ParamStore:
+    """(Re)build the flat parameter store for ``root``; idempotent while the trainable set and device are unchanged."""
+    st = getattr(root, "_prismer_store", None)
+    if st is not None and st.root is not root:
+        st = None
+    if device is None:
+        device = st.device if st is not None else torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if st is not None and st.device == device and st.signature == tuple(p.requires_grad for p in st.params) \
+            and st.params[0].data.device == device:
+        st.refresh()
+        return st
+    for b in root.buffers():
+        b.data = b.data.to(device)
+    return ParamStore(root, device)
+
+
+def _store(m: nn.Module) -> ParamStore:
+    st = getattr(m, "_prismer_store", None)
+    if st is None:
+        st = prepare(m)
+    return st
+
+
+# ======================================================================================================================
+# small helpers (forward / gradient plumbing)
+# ======================================================================================================================
+def _ln(x2d, ln: nn.LayerNorm, save: bool, out=None):
+    return ops.layernorm_fwd(x2d, ln.weight.data, ln.bias.data, ln.eps, save_stats=save, out=out)
+
+
+def _ln_bwd(dy, x, mean, rstd, ln, dres=None, dz=False, drop_p=0.0, seed=None, stream=0, need_dx=True):
+    tr = ln.weight.requires_grad
+    return ops.layernorm_bwd(dy, x, mean, rstd, ln.weight.data, dres=dres, dgamma=ln.weight._g32 if tr else None,
+                             dbeta=ln.bias._g32 if tr else None, need_dx=need_dx, dz=dz, drop_p=drop_p, seed=seed,
+                             rng_stream=stream)
+
+
+def _wgrad(dy2d, x2d, wg):
+    """wg[N_out, K_in] (fp32) += dy^T . x   (both operands MN-major: no transposes materialised)."""
+    if wg is not None:
+        gemm(dy2d, x2d, trans_a=True, trans_b=True, out=wg, accumulate=True)
+
+
+def _bgrad(dy2d, bg):
+    if bg is not None:
+        ops.colsum(dy2d, bg)
+
+
+def _lin_grads(dy2d, x2d, lin: nn.Linear):
+    if lin.weight.requires_grad:
+        _wgrad(dy2d, x2d, lin.weight._g32)
+        if lin.bias is not None:
+            _bgrad(dy2d, lin.bias._g32)
+
+
+def _mlp_fwd(x, fc: nn.Linear, proj: nn.Linear, act: str, residual, save: bool, drop_p=0.0, seed=None, stream=0, out=None):
+    z = torch.empty((x.shape[0], fc.weight.shape[0]), dtype=BF16, device=x.device) if save else None
+    a = gemm(x, fc.weight._c16, bias=fc.bias.data, act=act, aux_out=z)
+    y = gemm(a, proj.weight._c16, bias=proj.bias.data, residual=residual, drop_p=drop_p, seed=seed, rng_stream=stream, out=out)
+    return y, (z, a)
+
+
+def _mlp_bwd(dy, x, z, a, fc: nn.Linear, proj: nn.Linear, act: str):
+    """dy: gradient wrt (a.Wproj^T + b) [after any dropout mask was applied]; returns dx."""
+    dz = gemm(dy, proj.weight._c16, trans_b=True, act_grad=act, aux_in=z)
+    _lin_grads(dy, a, proj)
+    _lin_grads(dz, x, fc)
+    return gemm(dz, fc.weight._c16, trans_b=True)
+
+
+def _sf(t2d, L, B):
+    """seq-first 2-D rows (l*B+b) -> [B, L, C] strided view for the attention kernel."""
+    return t2d.view(L, B, t2d.shape[1]).transpose(0, 1)
+
+
+# ======================================================================================================================
+# encoder
+# ======================================================================================================================
+def _conv_out(h, s):
+    return (h - 1) // s + 1
+
+
+def _stem_fwd(stem, x, training: bool, save: bool):
+    B, Cin, Hl, Wl = x.shape
+    sf = stem.scale_factor
+    if sf != 1.0:
+        H, W = int(math.floor(Hl * sf)), int(math.floor(Wl * sf))
+        cur, nhwc = ops.resample_bilinear(x, H, W), True
+    else:
+        H, W, cur, nhwc = Hl, Wl, x, False
+    C = Cin
+    layers = []
+    scale = shift = None
+    for i, s in enumerate(stem.strides):
+        conv, bn = stem[str(1 + 3 * i)], stem[str(2 + 3 * i)]
+        wp = conv.weight._pack16
+        if i == 0 and Cin < 8:
+            A, Ho, Wo = ops.im2col_first(cur, nhwc, B, Cin, H, W, 3, s, wp.shape[1])
+        else:
+            A, Ho, Wo = ops.im2col_nhwc(cur, B, H, W, C, 3, s, scale, shift)
+        y = gemm(A, wp)
+        scale, shift, mean, rstd = ops.bn_stats(y, bn, training)
+        if training:
+            bn.num_batches_tracked += 1
+        layers.append(SimpleNamespace(A=A if save else None, y=y, scale=scale, shift=shift, mean=mean, rstd=rstd, H=H, W=W, C=C,
+                                      Ho=Ho, Wo=Wo, s=s))
+        cur, H, W, C = y, Ho, Wo, conv.weight.shape[0]
+    A5, _, _ = ops.im2col_nhwc(cur, B, H, W, C, 1, 1, scale, shift)
+    tok = gemm(A5, stem["13"].weight._pack16)
+    return tok, H, W, SimpleNamespace(layers=layers, A5=A5 if save else None, B=B)
+
+
+def _stem_bwd(stem, sv, dtok):
+    """dtok: [B*gh*gw, D] gradient wrt the stem's token output."""
+    B = sv.B
+    last = sv.layers[-1]
+    c13 = stem["13"]
+    _wgrad(dtok, sv.A5, c13.weight._g32.view(c13.weight.shape[0], -1) if c13.weight.requires_grad else None)
+    dA = gemm(dtok, c13.weight._pack16, trans_b=True)       # [M4, C4] = grad wrt relu(bn(y4))
+    ksz, s_next, Ho, Wo = 1, 1, last.Ho, last.Wo
+    for i in reversed(range(len(sv.layers))):
+        L = sv.layers[i]
+        conv, bn = stem[str(1 + 3 * i)], stem[str(2 + 3 * i)]
+        Cout = conv.weight.shape[0]
+        tr = bn.weight.requires_grad
+        dy = ops.bn_relu_bwd(dA, L.y, L.scale, L.shift, L.mean, L.rstd, bn.weight.data, bn.weight._g32 if tr else None,
+                             bn.bias._g32 if tr else None, B, L.Ho, L.Wo, Cout, ksz, s_next, Ho, Wo)
+        if conv.weight.requires_grad:
+            wp = conv.weight._pack16
+            dwp = torch.empty(wp.shape, dtype=F32, device=dy.device)
+            gemm(dy, L.A, trans_a=True, trans_b=True, out=dwp)
+            ops.conv_weight_unpack_grad(dwp, conv.weight._g32)
+        if i > 0:
+            dA = gemm(dy, conv.weight._pack16, trans_b=True)   # [M_i, 9*C_{i-1}] in (kh,kw,c) order
+            ksz, s_next, Ho, Wo = 3, L.s, L.Ho, L.Wo
+
+
+def _instance_table(inst: torch.Tensor) -> torch.Tensor:
+    """vit.py:144-146: one ``random.randint(0,127)`` per unique instance id in ascending order (consumes Python's
+    global ``random`` stream exactly like the reference).  Device presence flags -> 1 KiB D2H -> host table -> H2D."""
+    flags = ops.id_presence(inst).cpu()
+    table = torch.full((256,), -1, dtype=torch.int32)
+    for l in torch.nonzero(flags).flatten().tolist():
+        table[l] = random.randint(0, 127)
+    return table.to(inst.device)
+
+
+def _pos_for(vit, n_tok: int, save: bool):
+    """Positional embedding for a modality with n_tok tokens (vit.py:153-158): the table itself, or its bicubic
+    resize expressed as a fixed interpolation matrix applied with the GEMM kernel."""
+    pos = vit.positional_embedding
+    P = pos.shape[0]
+    if int(P ** 0.5) == int(n_tok ** 0.5):
+        return pos._c16, None
+    cache = vit.__dict__.setdefault("_interp", {})
+    key = (P, n_tok, str(pos.device))
+    if key not in cache:
+        from .modules.utils import interpolation_matrix
+        m = interpolation_matrix(P, n_tok)                     # [n_tok, P] fp32, host, built once
+        mp = torch.zeros((n_tok, (P + 7) // 8 * 8), dtype=BF16, device=pos.device)
+        mp[:, :P] = m.to(device=pos.device, dtype=BF16)
+        cache[key] = mp[:, :P]
+    W = cache[key]
+    return gemm(W, pos._c16, trans_b=True), W                 # [n_tok, D]
+
+
+def encoder_forward(vit, experts: Dict, save: bool):
+    """VisionTransformer.forward (vit.py:133-172).  Returns (out [S*B, D] seq-first rows, S, B, saved)."""
+    training = vit.training
+    D, p = vit.width, vit.patch_size
+    rgb = experts["rgb"]
+    B = rgb.shape[0]
+    dev = rgb.device
+    g = rgb.shape[2] // p
+    P = g * g
+    names = [e for e in experts if e != "rgb"]
+    has_res = len(names) > 0
+    S = P + (vit.resampler.latents.shape[0] if has_res else 0)
+    x0 = torch.empty((S * B, D), dtype=BF16, device=dev)
+    sv = SimpleNamespace(B=B, S=S, P=P, g=g, names=names, stems={}, experts=experts)
+
+    # rgb patch embedding (vit.py:86,153-155)
+    wr = vit.conv1["rgb"].weight
+    patches = ops.patchify(rgb, p, wr._pack16.shape[1])
+    tok = gemm(patches, wr._pack16)
+    pos_rgb, _ = _pos_for(vit, P, save)
+    ops.assemble_tokens(tok, pos_rgb, x0, D, B * D, B, P, D, g, g)
+    sv.patches = patches if save else None
+
+    if has_res:
+        toks = []
+        for e in names:
+            domain = "seg" if "seg" in e else e
+            xin = experts[e]["label"] if e == "obj_detection" else experts[e]
+            t, gh, gw, ssv = _stem_fwd(vit.conv1[domain], xin, training, save)
+            toks.append((e, domain, t, gh, gw, ssv))
+        N = sum(gh * gw for _, _, _, gh, gw, _ in toks)
+        xf = torch.empty((N * B, D), dtype=BF16, device=dev)
+        off = 0
+        sv.mods = []
+        for e, domain, t, gh, gw, ssv in toks:
+            n_e = gh * gw
+            pos_e, interp = _pos_for(vit, n_e, save)
+            inst = table = None
+            if e == "obj_detection":
+                inst = experts[e]["instance"]
+                table = _instance_table(inst)
+            ops.assemble_tokens(t, pos_e, xf[off * B:], D, B * D, B, n_e, D, gh, gw, inst, table,
+                                vit.instance_embedding._c16 if inst is not None else None)
+            sv.mods.append(SimpleNamespace(e=e, domain=domain, gh=gh, gw=gw, off=off, n=n_e, inst=inst, table=table, stem=ssv,
+                                           interp=interp))
+            off += n_e
+        sv.N = N
+        sv.res = _resampler_fwd(vit.resampler, xf, B, N, x0[P * B:], save)
+        sv.xf = xf if save else None
+
+    x, mu, rs = _ln(x0, vit.ln_pre, save)
+    sv.pre = (x0, mu, rs) if save else None
+    sv.blocks = []
+    for blk, adp in vit.transformer.resblocks:
+        x, bsv = _vit_block_fwd(blk, adp, x, B, S, save)
+        sv.blocks.append(bsv)
+    out, mu, rs = _ln(x, vit.ln_post, save)
+    sv.post = (x, mu, rs) if save else None
+    return out, S, B, sv
+
+
+def encoder_backward(vit, sv, dout):
+    """dout: [S*B, D] gradient wrt the encoder output (seq-first rows)."""
+    B, S, P, D = sv.B, sv.S, sv.P, vit.width
+    x, mu, rs = sv.post
+    dx, _ = _ln_bwd(dout, x, mu, rs, vit.ln_post)
+    for (blk, adp), bsv in zip(reversed(list(vit.transformer.resblocks)), reversed(sv.blocks)):
+        dx = _vit_block_bwd(blk, adp, dx, bsv, B, S)
+    x0, mu, rs = sv.pre
+    dx0, _ = _ln_bwd(dx, x0, mu, rs, vit.ln_pre)               # [S*B, D]
+    pos = vit.positional_embedding
+    pos_tr = pos.requires_grad
+    # rgb branch: positional embedding + patch conv weight
+    wr = vit.conv1["rgb"].weight
+    dtok = dx0[:P * B]
+    dsrc = torch.empty((B * P, D), dtype=BF16, device=dx0.device)
+    ops.assemble_tokens_bwd(dtok, D, B * D, dsrc, B, P, D, sv.g, sv.g)
+    if wr.requires_grad:
+        K = wr[0].numel()
+        if wr._pack16.shape[1] == K:
+            _wgrad(dsrc, sv.patches, wr._g32.view(D, K))
+        else:
+            tmp = torch.empty(wr._pack16.shape, dtype=F32, device=dx0.device)
+            gemm(dsrc, sv.patches, trans_a=True, trans_b=True, out=tmp)
+            ops.unpad_add(tmp, wr._g32.view(D, K))
+    if pos_tr:
+        _pos_grad(vit, dtok, B, P, D, 1, 0, None)
+    if not sv.names:
+        return
+    dxf = _resampler_bwd(vit.resampler, sv.res, dx0[P * B:], sv.xf, B, sv.N)      # [N*B, D]
+    ie = getattr(vit, "instance_embedding", None)
+    # all expert modalities share the positional embedding: one reduction over batch and modality slots when uniform
+    uniform = all(m.n == sv.mods[0].n for m in sv.mods)
+    if pos_tr and uniform:
+        _pos_grad(vit, dxf, B, sv.mods[0].n, D, len(sv.mods), sv.mods[0].n, sv.mods[0].interp)
+    for m in sv.mods:
+        dt = dxf[m.off * B:(m.off + m.n) * B]
+        if pos_tr and not uniform:
+            _pos_grad(vit, dt, B, m.n, D, 1, 0, m.interp)
+        dsrc = torch.empty((B * m.n, D), dtype=BF16, device=dx0.device)
+        ops.assemble_tokens_bwd(dt, D, B * D, dsrc, B, m.n, D, m.gh, m.gw, m.inst, m.table,
+                                ie._g32 if (m.inst is not None and ie.requires_grad) else None)
+        _stem_bwd(vit.conv1[m.domain], m.stem, dsrc)
+
+
+def _pos_grad(vit, dtok_sf, B, n_tok, D, n_slots, slot_stride, interp):
+    """positional-embedding gradient from seq-first token gradients (rows l*B+b)."""
+    pos = vit.positional_embedding
+    if interp is None:
+        ops.pos_grad(dtok_sf, D, B * D, B, n_tok, D, n_slots, slot_stride, pos._g32)
+    else:
+        tmp = torch.zeros((n_tok, D), dtype=F32, device=dtok_sf.device)
+        ops.pos_grad(dtok_sf, D, B * D, B, n_tok, D, n_slots, slot_stride, tmp)
+        t16 = torch.empty((n_tok, D), dtype=BF16, device=tmp.device)
+        ops.cast_bf16(tmp, t16)
+        gemm(interp, t16, trans_a=True, trans_b=True, out=pos._g32, accumulate=True)   # dpos += W^T . dpos_e
+
+
+# ---------------------------------------------------------------------------------------------------- ViT block
+def _vit_block_fwd(blk, adp, x, B, S, save):
+    D, H = x.shape[1], blk.n_head
+    at = blk.attn
+    h, mu1, rs1 = _ln(x, blk.ln_1, save)
+    qkv = gemm(h, at.in_proj_weight._c16, bias=at.in_proj_bias.data)
+    q3 = _sf(qkv, S, B)
+    o = torch.empty((S * B, D), dtype=BF16, device=x.device)
+    _, lse = ops.attention_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], H, need_lse=save, out=_sf(o, S, B))
+    x1 = gemm(o, at.out_proj.weight._c16, bias=at.out_proj.bias.data, residual=x)
+    h2, mu2, rs2 = _ln(x1, adp.adaptor_ln, save)
+    x2, (za, a) = _mlp_fwd(h2, adp.adaptor.down_proj, adp.adaptor.up_proj, "sqrelu", x1, save)
+    h3, mu3, rs3 = _ln(x2, blk.ln_2, save)
+    x3, (zf, f) = _mlp_fwd(h3, blk.mlp.c_fc, blk.mlp.c_proj, blk.mlp.act, x2, save)
+    sv = SimpleNamespace(x=x, mu1=mu1, rs1=rs1, h=h, qkv=qkv, o=o, lse=lse, x1=x1, mu2=mu2, rs2=rs2, h2=h2, za=za, a=a, x2=x2,
+                         mu3=mu3, rs3=rs3, h3=h3, zf=zf, f=f) if save else None
+    return x3, sv
+
+
+def _vit_block_bwd(blk, adp, dx3, sv, B, S):
+    D, H = dx3.shape[1], blk.n_head
+    at = blk.attn
+    dh3 = _mlp_bwd(dx3, sv.h3, sv.zf, sv.f, blk.mlp.c_fc, blk.mlp.c_proj, blk.mlp.act)
+    dx2, _ = _ln_bwd(dh3, sv.x2, sv.mu3, sv.rs3, blk.ln_2, dres=dx3)
+    dh2 = _mlp_bwd(dx2, sv.h2, sv.za, sv.a, adp.adaptor.down_proj, adp.adaptor.up_proj, "sqrelu")
+    dx1, _ = _ln_bwd(dh2, sv.x1, sv.mu2, sv.rs2, adp.adaptor_ln, dres=dx2)
+    do = gemm(dx1, at.out_proj.weight._c16, trans_b=True)
+    _lin_grads(dx1, sv.o, at.out_proj)
+    dqkv = torch.empty_like(sv.qkv)
+    q3, d3 = _sf(sv.qkv, S, B), _sf(dqkv, S, B)
+    ops.attention_bwd(_sf(do, S, B), q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], _sf(sv.o, S, B), sv.lse, H,
+                      dq=d3[..., :D], dk=d3[..., D:2 * D], dv=d3[..., 2 * D:])
+    if at.in_proj_weight.requires_grad:
+        _wgrad(dqkv, sv.h, at.in_proj_weight._g32)
+        _bgrad(dqkv, at.in_proj_bias._g32)
+    dh = gemm(dqkv, at.in_proj_weight._c16, trans_b=True)
+    dx, _ = _ln_bwd(dh, sv.x, sv.mu1, sv.rs1, blk.ln_1, dres=dx1)
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------------- resampler
+def _resampler_fwd(res, xf, B, N, out_lat, save):
+    """PerceiverResampler.forward (resampler.py:46-52); xf [N*B, D] seq-first; the last block writes its latents straight
+    into ``out_lat`` (the tail of the ViT input buffer: ``torch.cat([rgb, latents])`` of vit.py:165 for free)."""
+    Lr, D = res.latents.shape
+    H = res.heads
+    dev = xf.device
+    lat = torch.empty((Lr * B, D), dtype=BF16, device=dev)
+    ops.broadcast_rows(res.latents._c16, lat, D, B * D, B, Lr, D)
+    svs = []
+    nb = len(res.perceiver_blocks)
+    for li, blk in enumerate(res.perceiver_blocks):
+        at = blk.attn
+        kvin = torch.empty(((Lr + N) * B, D), dtype=BF16, device=dev)
+        _, mu1, rs1 = _ln(lat, blk.ln_1, save, out=kvin[:Lr * B])
+        _, mu2, rs2 = _ln(xf, blk.ln_2, save, out=kvin[Lr * B:])
+        W, bias = at.in_proj_weight._c16, at.in_proj_bias.data
+        q = gemm(kvin[:Lr * B], W[:D], bias=bias[:D])
+        kv = gemm(kvin, W[D:], bias=bias[D:])                                   # [(Lr+N)*B, 2D]
+        o = torch.empty((Lr * B, D), dtype=BF16, device=dev)
+        kv3 = _sf(kv, Lr + N, B)
+        _, lse = ops.attention_fwd(_sf(q, Lr, B), kv3[..., :D], kv3[..., D:], H, need_lse=save, out=_sf(o, Lr, B))
+        lat1 = gemm(o, at.out_proj.weight._c16, bias=at.out_proj.bias.data, residual=lat)
+        hff, mu3, rs3 = _ln(lat1, blk.ln_ff, save)
+        lat2, (zf, f) = _mlp_fwd(hff, blk.mlp.c_fc, blk.mlp.c_proj, "sqrelu", lat1, save, out=out_lat if li == nb - 1 else None)
+        if save:
+            svs.append(SimpleNamespace(lat=lat, mu1=mu1, rs1=rs1, mu2=mu2, rs2=rs2, kvin=kvin, q=q, kv=kv, o=o, lse=lse, lat1=lat1,
+                                       mu3=mu3, rs3=rs3, hff=hff, zf=zf, f=f))
+        lat = lat2
+    return svs
+
+
+def _resampler_bwd(res, svs, dlat, xf, B, N):
+    Lr, D = res.latents.shape
+    H = res.heads
+    dxf = None
+    for blk, sv in zip(reversed(list(res.perceiver_blocks)), reversed(svs)):
+        at = blk.attn
+        W = at.in_proj_weight._c16
+        dhff = _mlp_bwd(dlat, sv.hff, sv.zf, sv.f, blk.mlp.c_fc, blk.mlp.c_proj, "sqrelu")
+        dlat1, _ = _ln_bwd(dhff, sv.lat1, sv.mu3, sv.rs3, blk.ln_ff, dres=dlat)
+        do = gemm(dlat1, at.out_proj.weight._c16, trans_b=True)
+        _lin_grads(dlat1, sv.o, at.out_proj)
+        dq = torch.empty_like(sv.q)
+        dkv = torch.empty_like(sv.kv)
+        kv3, dkv3 = _sf(sv.kv, Lr + N, B), _sf(dkv, Lr + N, B)
+        ops.attention_bwd(_sf(do, Lr, B), _sf(sv.q, Lr, B), kv3[..., :D], kv3[..., D:], _sf(sv.o, Lr, B), sv.lse, H,
+                          dq=_sf(dq, Lr, B), dk=dkv3[..., :D], dv=dkv3[..., D:])
+        if at.in_proj_weight.requires_grad:
+            wg, bg = at.in_proj_weight._g32, at.in_proj_bias._g32
+            _wgrad(dq, sv.kvin[:Lr * B], wg[:D]); _bgrad(dq, bg[:D])
+            _wgrad(dkv, sv.kvin, wg[D:]); _bgrad(dkv, bg[D:])
+        dkvin = gemm(dkv, W[D:], trans_b=True)                                    # [(Lr+N)*B, D]
+        dql = gemm(dq, W[:D], trans_b=True, residual=dkvin[:Lr * B])              # grad wrt LN1(lat) (q path + kv path)
+        dlat, _ = _ln_bwd(dql, sv.lat, sv.mu1, sv.rs1, blk.ln_1, dres=dlat1)
+        dxf, _ = _ln_bwd(dkvin[Lr * B:], xf, sv.mu2, sv.rs2, blk.ln_2, dres=dxf)   # accumulates over the 4 blocks
+    if res.latents.requires_grad:
+        ops.reduce_batch(dlat, D, B * D, B, Lr, D, res.latents._g32)
+    return dxf
+
+
+# ======================================================================================================================
+# decoder
+# ======================================================================================================================
+def _enc_layout(enc: torch.Tensor):
+    """Accepts the encoder states as [B, S, Dv] with any of: seq-first storage (the encoder's own output, transposed
+    view), contiguous batch-first, fp32 or bf16.  Returns (flat [S*B or B*S, Dv] bf16, B, S, batch stride, row stride)
+    in units of *flat rows*."""
+    B, S, Dv = enc.shape
+    if enc.dtype != BF16:
+        src = enc.contiguous().float()
+        enc16 = torch.empty((B, S, Dv), dtype=BF16, device=enc.device)
+        ops.cast_bf16(src.view(-1), enc16.view(-1))
+        enc = enc16
+    if enc.stride(2) == 1 and enc.stride(0) == Dv and enc.stride(1) == B * Dv:
+        return enc.transpose(0, 1).reshape(S * B, Dv), B, S, 1, B          # seq-first storage: row = s*B + b
+    if not enc.is_contiguous():
+        c = torch.empty((B, S, Dv), dtype=BF16, device=enc.device)
+        for b in range(B):
+            ops.copy_rows(enc[b], c[b])
+        enc = c
+    return enc.view(B * S, Dv), B, S, S, 1                                  # batch-first: row = b*S + s
+
+
+def _x3(t2d, B, S, bs_rows, rs_rows, c0, c1):
+    """[B, S, c1-c0] strided view of columns [c0, c1) of flat rows with (batch, row) strides given in rows."""
+    ld = t2d.stride(0)
+    return torch.as_strided(t2d, (B, S, c1 - c0), (bs_rows * ld, rs_rows * ld, 1), t2d.storage_offset() + c0)
+
+
+def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: bool, need_logits: bool = True):
+    """RobertaForCausalLMModified.forward (roberta.py:358-399) on a batch of pre-tokenised ids."""
+    cfg = dec.config
+    st = _store(dec)
+    training = dec.training
+    p_h = cfg.hidden_dropout_prob if training else 0.0
+    p_a = cfg.attention_probs_dropout_prob if training else 0.0
+    seed = st.seed
+    B, T = input_ids.shape
+    Hd, nh, V = cfg.hidden_size, cfg.num_attention_heads, cfg.vocab_size
+    dev = input_ids.device
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)
+    attention_mask = attention_mask.to(torch.int64).contiguous()
+    input_ids = input_ids.contiguous()
+    emb = dec.roberta.embeddings
+    e, pos_ids = ops.embed_fwd(input_ids, emb.word_embeddings.weight._c16, emb.position_embeddings.weight._c16,
+                               emb.token_type_embeddings.weight._c16, cfg.pad_token_id)
+    h, mu, rs = _ln(e, emb.LayerNorm, save)          # embedding LayerNorm, then dropout (roberta.py:74-75)
+    sv = SimpleNamespace(B=B, T=T, ids=input_ids, mask=attention_mask, pos_ids=pos_ids, e=e, emu=mu, ers=rs, layers=[], p_h=p_h,
+                         p_a=p_a, labels=labels, weights=weights)
+    if p_h > 0:
+        h = ops.dropout(h, p_h, seed, _site(_RS_EMB, 0))
+    encoder = dec.roberta.encoder
+    L = len(encoder.layer)
+    enc_flat, Be, S, ebs, ers_ = _enc_layout(enc)
+    assert Be == B, "encoder_hidden_states batch mismatch"
+    xg = encoder._grp
+    kv_all = gemm(enc_flat, xg.w16, bias=xg.b)                                    # [S*B, L*2H] all cross K/V at once
+    sv.enc_flat, sv.kv_all, sv.S, sv.ebs, sv.ers = enc_flat, kv_all, S, ebs, ers_
+    for li, (layer, cross, adp) in enumerate(encoder.layer):
+        h, lsv = _dec_self_fwd(layer, h, B, T, nh, attention_mask, p_h, p_a, seed, li, save)
+        # cross attention over the visual tokens (roberta.py:225; no mask)
+        q = gemm(h, cross.self.query.weight._c16, bias=cross.self.query.bias.data)
+        k3 = _x3(kv_all, B, S, ebs, ers_, li * 2 * Hd, li * 2 * Hd + Hd)
+        v3 = _x3(kv_all, B, S, ebs, ers_, li * 2 * Hd + Hd, (li + 1) * 2 * Hd)
+        o = torch.empty((B * T, Hd), dtype=BF16, device=dev)
+        _, lse = ops.attention_fwd(q.view(B, T, Hd), k3, v3, nh, drop_p=p_a, seed=seed, rng_stream=_site(_RS_CROSS_P, li),
+                                   need_lse=save, out=o.view(B, T, Hd))
+        pre = gemm(o, cross.output.dense.weight._c16, bias=cross.output.dense.bias.data, residual=h, drop_p=p_h, seed=seed,
+                   rng_stream=_site(_RS_CROSS_O, li))
+        h_c, muc, rsc = _ln(pre, cross.output.LayerNorm, save)
+        # adaptor, norm-late (utils.py:61-62)
+        prea, (za, a) = _mlp_fwd(h_c, adp.adaptor.down_proj, adp.adaptor.up_proj, "sqrelu", h_c, save)
+        h_a, mua, rsa = _ln(prea, adp.adaptor_ln, save)
+        h, msv = _dec_mlp_fwd(layer, h_a, p_h, seed, li, save)
+        if save:
+            lsv.cross = SimpleNamespace(hin=lsv.hout, q=q, o=o, lse=lse, pre=pre, mu=muc, rs=rsc, h_c=h_c, za=za, a=a, prea=prea,
+                                        mua=mua, rsa=rsa, h_a=h_a)
+            lsv.mlp = msv
+            sv.layers.append(lsv)
+    h, osv = _dec_self_fwd(encoder.output_layer, h, B, T, nh, attention_mask, p_h, p_a, seed, L, save)
+    h, omsv = _dec_mlp_fwd(encoder.output_layer, h, p_h, seed, L, save)
+    sv.out_self, sv.out_mlp = osv, omsv
+    if not need_logits:
+        return h, None, None, sv
+    # LM head (roberta.py:421-426); logits kept fp32, leading dimension padded to a multiple of 8
+    lm = dec.lm_head
+    zh = torch.empty((B * T, Hd), dtype=BF16, device=dev) if save else None
+    g_ = gemm(h, lm.dense.weight._c16, bias=lm.dense.bias.data, act="gelu", aux_out=zh)
+    xl, mul, rsl = _ln(g_, lm.layer_norm, save)
+    Vp = (V + 7) // 8 * 8
+    logits_buf = torch.empty((B * T, Vp), dtype=F32, device=dev)
+    logits = logits_buf[:, :V]
+    gemm(xl, emb.word_embeddings.weight._c16, bias=lm.bias.data, out=logits)
+    sv.head = SimpleNamespace(h=h, zh=zh, g=g_, mu=mul, rs=rsl, xl=xl, logits=logits) if save else None
+    loss_mean = loss_samples = None
+    if labels is not None:
+        labels = labels.contiguous()
+        loss_mean, loss_samples, row_lse = ops.ce_loss_fwd(logits, labels, V, weights)
+        sv.row_lse = row_lse
+    return logits, loss_samples, loss_mean, sv
+
+
+def _dec_self_fwd(layer, h, B, T, nh, mask, p_h, p_a, seed, li, save):
+    at = layer.attention
+    Hd = h.shape[1]
+    grp = at.self._grp
+    qkv = gemm(h, grp.w16, bias=grp.b)                                            # fused q/k/v projection
+    q3 = qkv.view(B, T, 3 * Hd)
+    o = torch.empty((B * T, Hd), dtype=BF16, device=h.device)
+    _, lse = ops.attention_fwd(q3[..., :Hd], q3[..., Hd:2 * Hd], q3[..., 2 * Hd:], nh, causal=True, key_mask=mask, drop_p=p_a,
+                               seed=seed, rng_stream=_site(_RS_SELF_P, li), need_lse=save, out=o.view(B, T, Hd))
+    pre = gemm(o, at.output.dense.weight._c16, bias=at.output.dense.bias.data, residual=h, drop_p=p_h, seed=seed,
+               rng_stream=_site(_RS_SELF_O, li))
+    hout, mu, rs = _ln(pre, at.output.LayerNorm, save)
+    sv = SimpleNamespace(hin=h, qkv=qkv, o=o, lse=lse, pre=pre, mu=mu, rs=rs, hout=hout) if save else None
+    return hout, sv
+
+
+def _dec_mlp_fwd(layer, h, p_h, seed, li, save):
+    pre, (z, a) = _mlp_fwd(h, layer.intermediate.dense, layer.output.dense, "gelu", h, save, drop_p=p_h, seed=seed,
+                           stream=_site(_RS_MLP_O, li))
+    hout, mu, rs = _ln(pre, layer.output.LayerNorm, save)
+    return hout, (SimpleNamespace(hin=h, z=z, a=a, pre=pre, mu=mu, rs=rs) if save else None)
+
+
+def _dec_mlp_bwd(layer, dh, sv, p_h, seed, li):
+    dpre, dz_ = _ln_bwd(dh, sv.pre, sv.mu, sv.rs, layer.output.LayerNorm, dz=True, drop_p=p_h, seed=seed,
+                        stream=_site(_RS_MLP_O, li))
+    dhin_branch = _mlp_bwd(dz_, sv.hin, sv.z, sv.a, layer.intermediate.dense, layer.output.dense, "gelu")
+    return dpre, dhin_branch     # caller adds: d(hin) = dpre (residual) + branch
+
+
+def _add(a, b):
+    """a += b on bf16 [M, H] rows (gradient joins)."""
+    ops.copy_rows(b, a, add=True)
+    return a
+
+
+def _dec_self_bwd(layer, dh, sv, B, T, nh, mask, p_h, p_a, seed, li):
+    at = layer.attention
+    Hd = dh.shape[1]
+    grp = at.self._grp
+    dpre, dz_ = _ln_bwd(dh, sv.pre, sv.mu, sv.rs, at.output.LayerNorm, dz=True, drop_p=p_h, seed=seed, stream=_site(_RS_SELF_O, li))
+    do = gemm(dz_, at.output.dense.weight._c16, trans_b=True)
+    _lin_grads(dz_, sv.o, at.output.dense)
+    dqkv = torch.empty_like(sv.qkv)
+    q3, d3 = sv.qkv.view(B, T, 3 * Hd), dqkv.view(B, T, 3 * Hd)
+    ops.attention_bwd(do.view(B, T, Hd), q3[..., :Hd], q3[..., Hd:2 * Hd], q3[..., 2 * Hd:], sv.o.view(B, T, Hd), sv.lse, nh,
+                      causal=True, key_mask=mask, drop_p=p_a, seed=seed, rng_stream=_site(_RS_SELF_P, li),
+                      dq=d3[..., :Hd], dk=d3[..., Hd:2 * Hd], dv=d3[..., 2 * Hd:])
+    _wgrad(dqkv, sv.hin, grp.wg)
+    _bgrad(dqkv, grp.bg)
+    return gemm(dqkv, grp.w16, trans_b=True, residual=dpre)     # d(hin) = residual path + qkv path
+
+
+def decoder_backward(dec, sv, gscale: Optional[torch.Tensor] = None, dlogits: Optional[torch.Tensor] = None):
+    """Backward of ``decoder_forward`` from the (weighted) batch-mean loss; returns d(enc_flat) [rows as enc_flat]."""
+    cfg = dec.config
+    st = _store(dec)
+    seed = st.seed
+    B, T = sv.B, sv.T
+    Hd, nh, V = cfg.hidden_size, cfg.num_attention_heads, cfg.vocab_size
+    p_h, p_a = sv.p_h, sv.p_a
+    emb, lm, encoder = dec.roberta.embeddings, dec.lm_head, dec.roberta.encoder
+    L = len(encoder.layer)
+    hd = sv.head
+    if dlogits is None:
+        dlogits = ops.ce_loss_bwd(hd.logits, sv.labels, sv.row_lse, V, sv.weights, gscale)     # bf16 [B*T, Vp]
+    dl = dlogits[:, :V]
+    we = emb.word_embeddings.weight
+    if we.requires_grad:
+        _wgrad(dl, hd.xl, we._g32)                       # tied decoder weight (roberta.py:352-356)
+    if lm.bias.requires_grad:
+        _bgrad(dl, lm.bias._g32)
+    dxl = gemm(dl, we._c16, trans_b=True)
+    dg, _ = _ln_bwd(dxl, hd.g, hd.mu, hd.rs, lm.layer_norm)
+    dzh = ops.act_bwd(dg, hd.zh, "gelu")
+    _lin_grads(dzh, hd.h, lm.dense)
+    dh = gemm(dzh, lm.dense.weight._c16, trans_b=True)
+    # output layer
+    dpre, dbr = _dec_mlp_bwd(encoder.output_layer, dh, sv.out_mlp, p_h, seed, L)
+    dh = _add(dbr, dpre)
+    dh = _dec_self_bwd(encoder.output_layer, dh, sv.out_self, B, T, nh, sv.mask, p_h, p_a, seed, L)
+    dkv_all = torch.empty_like(sv.kv_all)      # every layer's backward fills its own [dK | dV] column slice
+    for li in reversed(range(L)):
+        layer, cross, adp = encoder.layer[li]
+        lsv = sv.layers[li]
+        c = lsv.cross
+        dpre, dbr = _dec_mlp_bwd(layer, dh, lsv.mlp, p_h, seed, li)
+        dh_a = _add(dbr, dpre)
+        # adaptor (norm late): h_a = LN(up(sqrelu(down(h_c))) + h_c)
+        dprea, _ = _ln_bwd(dh_a, c.prea, c.mua, c.rsa, adp.adaptor_ln)
+        dbr = _mlp_bwd(dprea, c.h_c, c.za, c.a, adp.adaptor.down_proj, adp.adaptor.up_proj, "sqrelu")
+        dh_c = _add(dbr, dprea)
+        # cross attention
+        dpre, dz_ = _ln_bwd(dh_c, c.pre, c.mu, c.rs, cross.output.LayerNorm, dz=True, drop_p=p_h, seed=seed,
+                            stream=_site(_RS_CROSS_O, li))
+        do = gemm(dz_, cross.output.dense.weight._c16, trans_b=True)
+        _lin_grads(dz_, c.o, cross.output.dense)
+        dq = torch.empty_like(c.q)
+        S, ebs, ers_ = sv.S, sv.ebs, sv.ers
+        k3 = _x3(sv.kv_all, B, S, ebs, ers_, li * 2 * Hd, li * 2 * Hd + Hd)
+        v3 = _x3(sv.kv_all, B, S, ebs, ers_, li * 2 * Hd + Hd, (li + 1) * 2 * Hd)
+        dk3 = _x3(dkv_all, B, S, ebs, ers_, li * 2 * Hd, li * 2 * Hd + Hd)
+        dv3 = _x3(dkv_all, B, S, ebs, ers_, li * 2 * Hd + Hd, (li + 1) * 2 * Hd)
+        ops.attention_bwd(do.view(B, T, Hd), c.q.view(B, T, Hd), k3, v3, c.o.view(B, T, Hd), c.lse, nh, drop_p=p_a, seed=seed,
+                          rng_stream=_site(_RS_CROSS_P, li), dq=dq.view(B, T, Hd), dk=dk3, dv=dv3)
+        _lin_grads(dq, c.hin, cross.self.query)
+        dh = gemm(dq, cross.self.query.weight._c16, trans_b=True, residual=dpre)
+        dh = _dec_self_bwd(layer, dh, lsv, B, T, nh, sv.mask, p_h, p_a, seed, li)
+    # grouped cross K/V projections of all layers: one wgrad, one dgrad
+    xg = encoder._grp
+    _wgrad(dkv_all, sv.enc_flat, xg.wg)
+    _bgrad(dkv_all, xg.bg)
+    denc = gemm(dkv_all, xg.w16, trans_b=True)                                   # [rows of enc_flat, Dv]
+    # embeddings
+    if p_h > 0:
+        dh = ops.dropout(dh, p_h, seed, _site(_RS_EMB, 0))
+    de, _ = _ln_bwd(dh, sv.e, sv.emu, sv.ers, emb.LayerNorm)
+    ops.embed_bwd(de, sv.ids, sv.pos_ids, we._g32 if we.requires_grad else None,
+                  emb.position_embeddings.weight._g32 if emb.position_embeddings.weight.requires_grad else None,
+                  emb.token_type_embeddings.weight._g32 if emb.token_type_embeddings.weight.requires_grad else None,
+                  cfg.pad_token_id)
+    return denc
+
+
+# ======================================================================================================================
+# public entry points used by the nn.Module surface
+# ======================================================================================================================
+def _experts_check(experts):
+    for k, v in experts.items():
+        ts = v.values() if isinstance(v, dict) else [v]
+        for t in ts:
+            if not t.is_cuda:
+                raise ops._C.PrismerError("prismer_b200 runs on CUDA tensors only (no CPU fallback): move the experts dict to the GPU")
+
+
+def encoder_apply(vit, experts: Dict) -> torch.Tensor:
+    """``VisionTransformer.forward``: inference-style call (no autograd graph); returns [S, B, D] bf16."""
+    _experts_check(experts)
+    _store(vit).refresh()
+    experts = {k: ({kk: vv.contiguous() for kk, vv in v.items()} if isinstance(v, dict) else v.float().contiguous())
+               for k, v in experts.items()}
+    out, S, B, _ = encoder_forward(vit, experts, save=False)
+    return out.view(S, B, -1)
+
+
+def decoder_apply(dec, input_ids, attention_mask, enc, labels=None, weights=None):
+    from .modules.roberta import CausalLMOutput
+    _store(dec).refresh()
+    logits, loss_samples, _, _ = decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save=False)
+    B, T = input_ids.shape
+    return CausalLMOutput(loss=loss_samples, logits=logits.unflatten(0, (B, T)))
+
+
+def standalone_layernorm(ln, x):
+    if not hasattr(ln.weight, "_c16"):
+        prepare(ln, x.device)
+    y, _, _ = ops.layernorm_fwd(x.to(BF16).contiguous(), ln.weight.data, ln.bias.data, ln.eps, save_stats=False)
+    return y.to(x.dtype)
+
+
+class _TrainStep(torch.autograd.Function):
+    """One node for the whole model: forward = engine forward (activations kept in ``ctx.sv``), backward = the
+    hand-written engine backward, which writes every parameter gradient into the flat fp32 buffer and publishes the
+    views as ``param.grad`` (so ``optimizer.step()`` of the reference loop keeps working)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, experts, input_ids, attention_mask, labels, weights):
+        st = _store(model)
+        st.refresh()
+        st.seed += 1
+        out, S, B, esv = encoder_forward(model.expert_encoder, experts, save=True)
+        enc = out.view(S, B, -1).transpose(0, 1)
+        _, loss_samples, loss_mean, dsv = decoder_forward(model.text_decoder, input_ids, attention_mask, enc, labels, weights, save=True)
+        ctx.model, ctx.esv, ctx.dsv = model, esv, dsv
+        return loss_mean.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        model = ctx.model
+        st = _store(model)
+        st.zero_grad()
+        gs = g.reshape(1).to(F32).contiguous()
+        denc = decoder_backward(model.text_decoder, ctx.dsv, gscale=gs)
+        encoder_backward(model.expert_encoder, ctx.esv, denc)
+        st.publish_grads()
+        ctx.esv = ctx.dsv = None
+        return (None,) * 7
+
+
+def train_loss(model, experts, input_ids, attention_mask, labels, weights=None) -> torch.Tensor:
+    _experts_check(experts)
+    st = _store(model)
+    anchor = st.train_params[0] if st.train_params else torch.zeros((), device=st.device, requires_grad=True)
+    experts = {k: ({kk: vv.contiguous() for kk, vv in v.items()} if isinstance(v, dict) else v.float().contiguous())
+               for k, v in experts.items()}
+    return _TrainStep.apply(anchor, model, experts, input_ids, attention_mask, labels, weights)

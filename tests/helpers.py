@@ -29,3 +29,27 @@ def rel_l2(a, b):
     a = torch.as_tensor(a).double().flatten()
     b = torch.as_tensor(b).double().flatten()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+class Holder(torch.nn.Module):
+    """expert_encoder + text_decoder pair with the reference's attribute names (a config-free ``Prismer``)."""
+
+    def __init__(self, enc, dec=None):
+        super().__init__()
+        self.expert_encoder = enc
+        if dec is not None:
+            self.text_decoder = dec
+
+
+def build_model(width, layers, patch, res, experts, dec_cfg, seed, device="cuda", freeze=None):
+    from prismer_b200 import modeling
+    enc = modeling.build_encoder(width, layers, patch, res, experts)
+    dec = modeling.build_decoder(dec_cfg) if dec_cfg is not None else None
+    m = Holder(enc, dec)
+    sd = synthetic.synth_state_dict(m.state_dict(), seed)
+    m.load_state_dict(sd)
+    if freeze == "freeze_vision":
+        for n, p in m.named_parameters():
+            p.requires_grad = not ("transformer.resblocks" in n and "adaptor" not in n)
+    m.to(device)
+    return m, sd
