@@ -294,6 +294,8 @@ def _stem_bwd(stem, sv, dtok):
         tr = bn.weight.requires_grad
         dy = ops.bn_relu_bwd(dA, L.y, L.scale, L.shift, L.mean, L.rstd, bn.weight.data, bn.weight._g32 if tr else None,
                              bn.bias._g32 if tr else None, B, L.Ho, L.Wo, Cout, ksz, s_next, Ho, Wo)
+        if getattr(sv, "debug", False):
+            L.dy, L.dA = dy, dA
         if conv.weight.requires_grad:
             wp = conv.weight._pack16
             dwp = torch.empty(wp.shape, dtype=F32, device=dy.device)
@@ -610,7 +612,7 @@ def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: 
     assert Be == B, "encoder_hidden_states batch mismatch"
     xg = encoder._grp
     kv_all = gemm(enc_flat, xg.w16, bias=xg.b)                                    # [S*B, L*2H] all cross K/V at once
-    sv.enc_flat, sv.kv_all, sv.S, sv.ebs, sv.ers = enc_flat, kv_all, S, ebs, ers_
+    sv.enc_flat, sv.kv_all, sv.S, sv.enc_bs, sv.enc_rs = enc_flat, kv_all, S, ebs, ers_
     for li, (layer, cross, adp) in enumerate(encoder.layer):
         h, lsv = _dec_self_fwd(layer, h, B, T, nh, attention_mask, p_h, p_a, seed, li, save)
         # cross attention over the visual tokens (roberta.py:225; no mask)
@@ -753,7 +755,7 @@ def decoder_backward(dec, sv, gscale: Optional[torch.Tensor] = None, dlogits: Op
         do = gemm(dz_, cross.output.dense.weight._c16, trans_b=True)
         _lin_grads(dz_, c.o, cross.output.dense)
         dq = torch.empty_like(c.q)
-        S, ebs, ers_ = sv.S, sv.ebs, sv.ers
+        S, ebs, ers_ = sv.S, sv.enc_bs, sv.enc_rs
         k3 = _x3(sv.kv_all, B, S, ebs, ers_, li * 2 * Hd, li * 2 * Hd + Hd)
         v3 = _x3(sv.kv_all, B, S, ebs, ers_, li * 2 * Hd + Hd, (li + 1) * 2 * Hd)
         dk3 = _x3(dkv_all, B, S, ebs, ers_, li * 2 * Hd, li * 2 * Hd + Hd)

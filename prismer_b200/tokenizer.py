@@ -60,6 +60,9 @@ class HashTokenizer:
 def build_tokenizer(model_name: str, vocab_size: int):
     try:
         from transformers import RobertaTokenizer
-        return RobertaTokenizer.from_pretrained(model_name, local_files_only=True)
+        tok = RobertaTokenizer.from_pretrained(model_name, local_files_only=True)
+        if tok.vocab_size < vocab_size - 16 or tok.pad_token_id != 1:   # transformers >= 5 returns an empty tokenizer
+            raise RuntimeError("no local vocabulary")
+        return tok
     except Exception:
         return HashTokenizer(vocab_size)
