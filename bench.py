@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the Prismer-BASE caption fine-tune step (BASELINE.json metric: caption-train images/sec at 1/2/4/8 B200).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a engine (one rank per GPU under torchrun)
+  python bench.py --impl reference ...                     # the reference's CPU PyTorch path (oracle port), rank 0 only
+  python bench.py --mode caption ...                       # greedy captions/sec (BASELINE config 2) instead of the train step
+
+A "step" is one fine-tune step of Prismer-BASE (6 experts, 224 px, T = 30, freeze_vision, dropout 0.1, AdamW lr 5e-5 wd 0.05)
+on a per-GPU batch of 32 synthetic images: forward + backward + ONE gradient all-reduce + optimizer.  Weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EXPERTS = ["depth", "normal", "seg_coco", "edge", "obj_detection", "ocr_detection"]
+TRAIN_GFLOP_PER_IMG = 263.1      # BASELINE.md section 3 / SURVEY.md section 8d (freeze_vision, T = 30)
+FWD_GFLOP_PER_IMG = 102.4
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm_gbs=d["hbm_gbs"], source="measured")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        top = sorted(sm)[len(sm) // 4:] if sm else []       # samples under load (drop the idle quartile)
+        return {"sm_mhz": statistics.median(top) if top else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def build_inputs(batch, seed, T=30):
+    from prismer_b200 import synthetic
+    ex = synthetic.synth_experts(batch, 224, EXPERTS, 224, seed)
+    ids, mask = synthetic.synth_tokens(batch, T, 50265, seed)
+    return ex, ids, mask
+
+
+def pin(experts):
+    out = {}
+    for k, v in experts.items():
+        out[k] = {kk: vv.pin_memory() for kk, vv in v.items()} if isinstance(v, dict) else v.pin_memory()
+    return out
+
+
+def nbytes(experts):
+    n = 0
+    for v in experts.values():
+        for t in (v.values() if isinstance(v, dict) else [v]):
+            n += t.numel() * t.element_size()
+    return n
+
+
+# ----------------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from prismer_b200 import _C, engine, ops, synthetic
+    from prismer_b200.accelerate_shim import allreduce_gradients
+    from prismer_b200.optim import FusedAdamW
+    from prismer_b200.prismer_caption import PrismerCaption
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    torch.manual_seed(0)
+    cfg = {"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": 224, "freeze": "freeze_vision"}
+    model = PrismerCaption(cfg)
+    model.to(dev)
+    st = engine.prepare(model, dev)
+    if world > 1:
+        dist.broadcast(st.master_t, 0); dist.broadcast(st.master_f, 0); st.refresh(force=True)
+    opt = FusedAdamW(model, lr=5e-5, weight_decay=0.05, grad_scale=1.0 / world)
+    ex_h, ids_h, mask_h = build_inputs(B, 1000 + rank)
+    ex_h = pin(ex_h); ids_h, mask_h = ids_h.pin_memory(), mask_h.pin_memory()
+    ex_d = synthetic.experts_to(ex_h, dev); ids_d, mask_d = ids_h.to(dev), mask_h.to(dev)
+    h2d = nbytes(ex_h) + ids_h.numel() * 8 + mask_h.numel() * 8
+
+    if args.mode == "caption":
+        return run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d)
+
+    model.train()
+
+    def step(ex, ids, mask):
+        loss = model(ex, input_ids=ids, attention_mask=mask, prompt_length=4)
+        opt.zero_grad()
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(model)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(args.warmup):
+        loss = step(ex_d, ids_d, mask_d)
+    c0 = _C.CALLS
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda: step(ex_d, ids_d, mask_d), args.steps)
+    launches = (_C.CALLS - c0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end through the public API with HOST inputs: pinned H2D of the step's inputs + D2H of the loss every step
+    def e2e_step():
+        ex = synthetic.experts_to(ex_h, dev, non_blocking=True)
+        l = step(ex, ids_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True))
+        return l.item()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, max(2, args.steps // 2)) / max(2, args.steps // 2)
+
+    # roofline pass: CUDA events around every GEMM launch of one step (the dominant kernel family)
+    ops.GEMM_PROFILE = []
+    step(ex_d, ids_d, mask_d)
+    torch.cuda.synchronize()
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    g_ms = sum(a.elapsed_time(b) for *_, a, b in prof)
+    g_flop = sum(2.0 * M * N * K for M, N, K, *_ in prof)
+    t0 = time.time(); step(ex_d, ids_d, mask_d); torch.cuda.synchronize()
+
+    if rank != 0:
+        return
+    pk = peaks()
+    ms_step = ms / args.steps
+    ips = world * B / (ms_step / 1e3)
+    achieved = g_flop / (g_ms / 1e3) / 1e12
+    out = {
+        "metric": "Prismer-BASE caption-train images/sec", "value": round(ips, 2), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Prismer-BASE caption fine-tune step (fwd+bwd+1 grad all-reduce+AdamW), 224x224 + 6 expert maps, "
+                               "T=30, freeze_vision, dropout 0.1", "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}", "l2": "per-step inputs (1.28 GB/GPU) exceed the 126 MB L2"},
+        "e2e": {"value": round(world * B / (ms_e2e / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(achieved, 1), "peak": pk["bf16_tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4), "traffic": None,
+                     "peak_source": pk["source"] + " sustained cuBLAS bf16", "gemm_launches_per_step": len(prof),
+                     "gemm_ms_per_step": round(g_ms, 3), "gemm_share_of_step": round(g_ms / ms_step, 3)},
+        "step_mfu": {"model_gflop_per_img": TRAIN_GFLOP_PER_IMG, "achieved_tflops_per_gpu": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3, 1),
+                     "frac_of_peak": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3 / pk["bf16_tflops_sustained"], 4)},
+        "loss": float(loss),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_train_baseline(model, sample_batch=2, iters=2)
+    print(json.dumps(out), flush=True)
+
+
+def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):
+    """Greedy captions/sec (BASELINE config 2): encoder + greedy decode (max_length 20, min_length 8, 4-token prefix)."""
+    import torch.distributed as dist
+    from prismer_b200 import _C, synthetic
+    model.eval()
+    B = args.batch
+    prefix = torch.tensor([[0, 250, 2170, 9]], device=dev).repeat(B, 1)
+
+    def cap(ex):
+        with torch.no_grad():
+            enc = model.expert_encoder(ex).transpose(0, 1)
+            return model.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=20, min_length=8)
+
+    for _ in range(args.warmup):
+        cap(ex_d)
+    torch.cuda.synchronize()
+    c0 = _C.CALLS
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = cap(ex_d)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e0.record()
+    for _ in range(max(2, args.steps // 2)):
+        o = cap(synthetic.experts_to(ex_h, dev, non_blocking=True)).cpu()
+    e1.record(); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / max(2, args.steps // 2)
+    if rank == 0:
+        print(json.dumps({"metric": "Prismer-BASE greedy captions/sec", "value": round(world * B / (float(t) / 1e3), 2), "unit": "captions/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(t), 3),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "Prismer-BASE caption inference, 224x224 + 6 expert maps, greedy max_length 20",
+                                     "per_gpu_batch": B},
+                          "e2e": {"value": round(world * B / (ms2 / 1e3), 2), "unit": "captions/s", "h2d_bytes_per_step": h2d,
+                                  "d2h_bytes_per_step": int(o.numel() * 8)},
+                          "gpu_launches": (_C.CALLS - c0) // args.steps}), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------- CPU arms
+def cpu_train_baseline(model, sample_batch=2, iters=2, threads=None):
+    """The reference's CPU PyTorch path (oracle port: same modules' math, fp32, eager) on a bounded sample of the workload."""
+    from oracle import prismer_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+    ex, ids, mask = build_inputs(sample_batch, 7)
+    train_keys = {n for n, p in model.named_parameters() if p.requires_grad}
+    for k, v in sd.items():
+        if k in train_keys:
+            v.requires_grad_(True)
+    times = []
+    for i in range(iters + 1):
+        t0 = time.time()
+        loss, _, _ = O.caption_train_loss(ex, ids, mask, 4, sd, 16, 12, training_bn=True)
+        loss.backward()
+        for v in sd.values():
+            v.grad = None
+        times.append(time.time() - t0)
+    t = statistics.median(times[1:])
+    return {"value": round(sample_batch / t, 3), "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{iters} fwd+bwd steps of batch {sample_batch} (same BASE config, fp32 eager PyTorch on the host), {t:.1f} s/step"}
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from prismer_b200.prismer_caption import PrismerCaption
+    torch.manual_seed(0)
+    cfg = {"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": 224, "freeze": "freeze_vision"}
+    model = PrismerCaption(cfg)          # parameter container only (CPU); the arithmetic below is the oracle port
+    sb = 2
+    t0 = time.time()
+    base = cpu_train_baseline(model, sample_batch=sb, iters=max(1, min(args.steps, 3)))
+    ips = base["value"]
+    print(json.dumps({"impl": "reference", "metric": "Prismer-BASE caption-train images/sec", "value": ips, "unit": "images/s",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sb / ips, 1),
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "Prismer-BASE caption fine-tune step on the host CPU (reference modules' math, eager fp32)",
+                                 "per_gpu_batch": sb},
+                      "cpu_baseline": base,
+                      "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "caption"])
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

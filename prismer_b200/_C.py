@@ -60,7 +60,12 @@ def _declare(L):
     _C_decl.declare(L)
 
 
+CALLS = 0   # number of C-ABI calls issued (each enqueues >= 1 kernel); bench.py reports it as gpu_launches
+
+
 def check(rc: int, what: str = ""):
+    global CALLS
+    CALLS += 1
     if rc != 0:
         raise PrismerError(f"libprismer_sm100 {what} failed: {ERRORS.get(rc, rc)} (code {rc})")
 

@@ -7,10 +7,16 @@ from typing import Optional
 import torch
 
 from . import _C
-from ._C import GemmArgs, check
+from ._C import GemmArgs
+
+GEMM_PROFILE = None   # set to a list to record (M, N, K, start_event, end_event) per GEMM launch (bench.py roofline pass)
 
 ACT = {"none": 0, None: 0, "quickgelu": 1, "gelu": 2, "sqrelu": 3, "relu": 4}
 BF16, F32 = torch.bfloat16, torch.float32
+
+
+def check(rc, what=""):
+    _C.check(rc, what)
 
 
 def _stream() -> int:
@@ -81,6 +87,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
         args.seed = seed.data_ptr()
     args.rng_stream = rng_stream
     args.force_bn, args.max_ctas = force_bn, max_ctas
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_C.lib().prismer_gemm_bf16(ctypes.byref(args), _stream()), "gemm_bf16")
+        e1.record()
+        GEMM_PROFILE.append((M, N, K, e0, e1))
+        return out
     check(_C.lib().prismer_gemm_bf16(ctypes.byref(args), _stream()), "gemm_bf16")
     return out
 

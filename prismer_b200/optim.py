@@ -1,0 +1,41 @@
+"""Fused AdamW over the engine's flat buffers -- the B200-side of ``optimizer.step()`` (train_caption.py:111-112,133).
+
+Same update rule as ``torch.optim.AdamW(lr, weight_decay)`` with torch defaults (betas (0.9, 0.999), eps 1e-8, decoupled
+weight decay applied to every trainable parameter, no parameter groups -- exactly what the reference loop builds); one
+kernel updates the fp32 masters, both moments and the bf16 compute copies, and folds in the 1/world gradient average."""
+from __future__ import annotations
+
+import torch
+
+from . import engine, ops
+
+
+class FusedAdamW:
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+        self.model = model
+        self.store = engine.prepare(model)
+        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self.param_groups = [dict(self.defaults, params=self.store.train_params)]   # LR schedules poke param_groups[i]['lr']
+        self.m = torch.zeros_like(self.store.master_t)
+        self.v = torch.zeros_like(self.store.master_t)
+        self.t = 0
+        self.grad_scale = grad_scale
+
+    def zero_grad(self, set_to_none: bool = True):
+        """Gradients live in one flat buffer that the engine's backward overwrites; nothing to do per parameter."""
+        return None
+
+    @torch.no_grad()
+    def step(self):
+        st = self.store
+        g = self.param_groups[0]
+        self.t += 1
+        ops.adamw_step(st.master_t, st.grad_t, self.m, self.v, st.c16_t, g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                       g["weight_decay"], self.t, self.grad_scale)
+        st.mark_fresh()
+
+    def state_dict(self):
+        return {"m": self.m, "v": self.v, "t": self.t, "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = sd["t"]
