@@ -190,9 +190,18 @@ def run_ours(args):
     step(ex_d, ids_d, mask_d)
     torch.cuda.synchronize()
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    if os.environ.get("PRISMER_BENCH_DUMP"):
+        agg = {}
+        for M, N, K, a, b in prof:
+            t = agg.setdefault((M, N, K), [0, 0.0]); t[0] += 1; t[1] += a.elapsed_time(b)
+        rows = sorted(([k, v[0], v[1], 2.0 * k[0] * k[1] * k[2] * v[0] / v[1] / 1e9] for k, v in agg.items()), key=lambda r: -r[2])
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "gemm_shapes.txt"), "w") as f:
+            for k, n, ms_, tf in rows:
+                f.write(f"M{k[0]:7d} N{k[1]:6d} K{k[2]:7d}  n={n:3d}  {ms_:8.3f} ms  {tf:8.1f} TF/s\n")
     g_ms = sum(a.elapsed_time(b) for *_, a, b in prof)
     g_flop = sum(2.0 * M * N * K for M, N, K, *_ in prof)
-    t0 = time.time(); step(ex_d, ids_d, mask_d); torch.cuda.synchronize()
+    torch.cuda.synchronize(); t0 = time.time(); step(ex_d, ids_d, mask_d); host_ms = (time.time() - t0) * 1e3; torch.cuda.synchronize()
 
     if rank != 0:
         return
@@ -216,6 +225,7 @@ def run_ours(args):
                      "gemm_ms_per_step": round(g_ms, 3), "gemm_share_of_step": round(g_ms / ms_step, 3)},
         "step_mfu": {"model_gflop_per_img": TRAIN_GFLOP_PER_IMG, "achieved_tflops_per_gpu": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3, 1),
                      "frac_of_peak": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3 / pk["bf16_tflops_sustained"], 4)},
+        "host_enqueue_ms_per_step": round(host_ms, 2),
         "loss": float(loss),
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -68,6 +68,7 @@ typedef struct PrismerGemmArgs {
   uint32_t rng_stream;     /* distinguishes dropout call sites */
   int force_bn;            /* 0 = heuristic, else 64 / 128 / 256 */
   int max_ctas;            /* 0 = number of SMs */
+  int force_splits;        /* 0 = heuristic split-K (fp32 accumulate outputs only), 1 = off, n = request n splits */
 } PrismerGemmArgs;
 
 int prismer_gemm_bf16(const PrismerGemmArgs* args, cudaStream_t stream);

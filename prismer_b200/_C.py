@@ -29,7 +29,7 @@ class GemmArgs(Structure):
         ("aux_out", c_void_p), ("aux_in", c_void_p), ("ldaux", c_longlong),
         ("act", c_int), ("act_grad", c_int), ("out_fp32", c_int), ("accumulate", c_int),
         ("alpha", c_float), ("drop_p", c_float), ("seed", c_void_p), ("rng_stream", c_uint32),
-        ("force_bn", c_int), ("max_ctas", c_int),
+        ("force_bn", c_int), ("max_ctas", c_int), ("force_splits", c_int),
     ]
 
 

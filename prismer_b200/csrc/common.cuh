@@ -87,17 +87,24 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-struct __align__(16) bf16x8 { __nv_bfloat162 v[4]; };
+// 8 bf16 moved as ONE 128-bit access (a struct of four bfloat162 compiles to four 32-bit accesses: 4x the LSU work and,
+// for row-strided epilogue stores, 4x the partial-sector writes).
+typedef uint4 bf16x8;
 
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
+  const uint32_t w[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(p.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ bf16x8 pack8(const float* f) {
-  bf16x8 p;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  return p;
+  return make_uint4(pack_bf162(f[0], f[1]), pack_bf162(f[2], f[3]), pack_bf162(f[4], f[5]), pack_bf162(f[6], f[7]));
 }
 
 static inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? PRISMER_OK : PRISMER_ERR_CUDA; }

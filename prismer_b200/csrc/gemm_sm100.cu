@@ -47,7 +47,7 @@ struct EpiParams {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                 EpiParams ep) {
+                 int splits, EpiParams ep) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -62,6 +62,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
+  // split-K (wgrad with few output tiles and a long contraction): work item w -> (tile = w % num_tiles, split = w / num_tiles),
+  // each split owns k-blocks [split*kps, min(num_k, (split+1)*kps)) and red.adds its partial tile into the fp32 output.
+  const int kps = (num_k + splits - 1) / splits;
+  const int num_work = num_tiles * splits;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -80,9 +84,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w % num_tiles, split = w / num_tiles;
         const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + C::kABytes;
@@ -111,11 +117,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int split = w / num_tiles;
+      const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
       ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);   // epilogue has drained this accumulator stage
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_k; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         if (lane == 0) {
@@ -129,10 +137,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                      : ptx::make_smem_desc_sw128(sa + kk * (UMMA_K * 2), 16, 1024);
             const uint64_t db = B_MN ? ptx::make_smem_desc_sw128(sb + kk * (UMMA_K * 128), BK * 128, 1024)
                                      : ptx::make_smem_desc_sw128(sb + kk * (UMMA_K * 2), 16, 1024);
-            ptx::umma_f16(tmem_d, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+            ptx::umma_f16(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
-          if (kb == num_k - 1) ptx::umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+          if (kb == kb1 - 1) ptx::umma_commit(&tmem_full[acc]);    // accumulator ready for the epilogue
         }
         __syncwarp();
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -147,7 +155,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     unsigned long long seed = 0;
     if (has_drop) seed = *ep.seed;
     const Philox philox(seed);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int tile = w % num_tiles;
       const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
       ptx::mbar_wait(&tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
@@ -229,7 +238,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // ---- store
           if (ep.out_fp32) {
             float* cp = reinterpret_cast<float*>(ep.C) + static_cast<long long>(row) * ep.ldc + col0;
-            if (full) {
+            if (splits > 1) {   // partial tile of a split-K work item: vector reduction into the fp32 output
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(cp + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (col0 + j < N) atomicAdd(cp + j, v[j]);
+              }
+            } else if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -310,7 +327,7 @@ int num_sms() {
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep, int max_ctas,
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int splits, const EpiParams& ep, int max_ctas,
            cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
   static bool configured = false;  // per-instantiation; benign race (idempotent)
@@ -319,25 +336,43 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
     if (e != cudaSuccess) return PRISMER_ERR_CUDA;
     configured = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   int grid = tiles < max_ctas ? tiles : max_ctas;
-  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, splits, ep);
   return LAUNCH_CHECK();
 }
 
-int pick_bn(int M, int N, int sms) {
-  // minimise (waves x per-tile cost); per-tile cost ~ BN + fixed overhead (pipeline fill + epilogue tail)
+// Cost model fitted to B200 measurements (tools/bench_gemm.py): the single-CTA mainloop is bound by L2->SM operand traffic,
+// ~(500 + 1.3*BN) cycles per 64-wide k-block, plus a per-tile epilogue/drain of ~(1500 + 4*BN) cycles that only partly overlaps.
+double tile_cost(int bn, int num_k) { return num_k * (500.0 + 1.3 * bn) + 1500.0 + 4.0 * bn; }
+
+void pick_config(int M, int N, int K, int sms, bool can_split, int* bn_out, int* splits_out) {
   const int cand[3] = {256, 128, 64};
-  int best = 128; double best_t = 1e30;
+  const int num_k = (K + BK - 1) / BK;
+  double best_t = 1e300;
+  int best_bn = 128, best_s = 1;
   for (int i = 0; i < 3; ++i) {
     const int bn = cand[i];
     if (bn > 64 && N <= bn / 2) continue;
     const long long tiles = static_cast<long long>((M + BM - 1) / BM) * ((N + bn - 1) / bn);
-    const long long waves = (tiles + sms - 1) / sms;
-    const double t = static_cast<double>(waves) * (bn + 48.0);
-    if (t < best_t) { best_t = t; best = bn; }
+    int max_s = 1;
+    if (can_split && tiles < sms) {
+      max_s = num_k / 4;                                     // keep >= 4 k-blocks per split
+      const int want = static_cast<int>((2LL * sms + tiles - 1) / tiles);
+      if (max_s > want) max_s = want;
+      if (max_s < 1) max_s = 1;
+    }
+    for (int s = 1; s <= max_s; s = (s < 4 ? s + 1 : s + s / 2)) {
+      const int kps = (num_k + s - 1) / s;
+      const int s_eff = (num_k + kps - 1) / kps;
+      const long long work = tiles * s_eff;
+      const long long waves = (work + sms - 1) / sms;
+      const double t = waves * tile_cost(bn, kps) + (s_eff > 1 ? 600.0 : 0.0);
+      if (t < best_t) { best_t = t; best_bn = bn; best_s = s_eff; }
+    }
   }
-  return best;
+  *bn_out = best_bn;
+  *splits_out = best_s;
 }
 
 }  // namespace
@@ -357,7 +392,21 @@ extern "C" int prismer_gemm_bf16(const PrismerGemmArgs* a, cudaStream_t stream) 
   if (a->residual && (a->ldr % 8)) return PRISMER_ERR_ALIGN;
   if ((a->aux_out || a->aux_in) && (a->ldaux % 8)) return PRISMER_ERR_ALIGN;
 
-  int bn = a->force_bn ? a->force_bn : pick_bn(a->M, a->N, num_sms());
+  // split-K only for plain fp32 accumulation (wgrad): partial tiles are red.added, so no epilogue op may be attached
+  const bool can_split = a->out_fp32 && a->accumulate && !a->bias && !a->residual && !a->aux_out && !a->aux_in && !a->act &&
+                         !a->act_grad && a->drop_p == 0.f && a->force_splits != 1;
+  int bn = 0, splits = 1;
+  pick_config(a->M, a->N, a->K, num_sms(), can_split, &bn, &splits);
+  if (a->force_bn) {
+    bn = a->force_bn;
+    splits = 1;
+    if (can_split) { int dummy; pick_config(a->M, a->N, a->K, num_sms(), true, &dummy, &splits); }
+  }
+  if (a->force_splits > 1 && can_split) {
+    const int num_k = (a->K + BK - 1) / BK;
+    const int kps = (num_k + a->force_splits - 1) / a->force_splits;
+    splits = (num_k + kps - 1) / kps;
+  }
   if (bn != 64 && bn != 128 && bn != 256) return PRISMER_ERR_SHAPE;
 
   CUtensorMap ta, tb;
@@ -387,10 +436,10 @@ extern "C" int prismer_gemm_bf16(const PrismerGemmArgs* a, cudaStream_t stream) 
 
   const int sms = a->max_ctas > 0 ? a->max_ctas : num_sms();
 #define DISPATCH(BN_)                                                                       \
-  if (!a->transA && !a->transB) return launch<BN_, false, false>(ta, tb, a->M, a->N, a->K, ep, sms, stream); \
-  if (!a->transA && a->transB) return launch<BN_, false, true>(ta, tb, a->M, a->N, a->K, ep, sms, stream);   \
-  if (a->transA && !a->transB) return launch<BN_, true, false>(ta, tb, a->M, a->N, a->K, ep, sms, stream);   \
-  return launch<BN_, true, true>(ta, tb, a->M, a->N, a->K, ep, sms, stream);
+  if (!a->transA && !a->transB) return launch<BN_, false, false>(ta, tb, a->M, a->N, a->K, splits, ep, sms, stream); \
+  if (!a->transA && a->transB) return launch<BN_, false, true>(ta, tb, a->M, a->N, a->K, splits, ep, sms, stream);   \
+  if (a->transA && !a->transB) return launch<BN_, true, false>(ta, tb, a->M, a->N, a->K, splits, ep, sms, stream);   \
+  return launch<BN_, true, true>(ta, tb, a->M, a->N, a->K, splits, ep, sms, stream);
   if (bn == 256) { DISPATCH(256) }
   if (bn == 128) { DISPATCH(128) }
   DISPATCH(64)

@@ -298,8 +298,8 @@ def _stem_bwd(stem, sv, dtok):
             L.dy, L.dA = dy, dA
         if conv.weight.requires_grad:
             wp = conv.weight._pack16
-            dwp = torch.empty(wp.shape, dtype=F32, device=dy.device)
-            gemm(dy, L.A, trans_a=True, trans_b=True, out=dwp)
+            dwp = torch.zeros(wp.shape, dtype=F32, device=dy.device)
+            gemm(dy, L.A, trans_a=True, trans_b=True, out=dwp, accumulate=True)    # accumulate => split-K eligible (K = B*Ho*Wo)
             ops.conv_weight_unpack_grad(dwp, conv.weight._g32)
         if i > 0:
             dA = gemm(dy, conv.weight._pack16, trans_b=True)   # [M_i, 9*C_{i-1}] in (kh,kw,c) order

@@ -43,7 +43,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
          aux_out: Optional[torch.Tensor] = None, aux_in: Optional[torch.Tensor] = None, act_grad=0,
          out: Optional[torch.Tensor] = None, out_dtype=BF16, accumulate: bool = False, alpha: float = 1.0,
          drop_p: float = 0.0, seed: Optional[torch.Tensor] = None, rng_stream: int = 0, force_bn: int = 0,
-         max_ctas: int = 0) -> torch.Tensor:
+         max_ctas: int = 0, force_splits: int = 0) -> torch.Tensor:
     """C[M,N] = epilogue(alpha * op(A) . op(B)^T); A is [M,K] (or [K,M] if trans_a), B is [N,K] (or [K,N] if trans_b)."""
     _req_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16
@@ -86,7 +86,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
         assert seed is not None and seed.dtype == torch.int64 and seed.is_cuda
         args.seed = seed.data_ptr()
     args.rng_stream = rng_stream
-    args.force_bn, args.max_ctas = force_bn, max_ctas
+    args.force_bn, args.max_ctas, args.force_splits = force_bn, max_ctas, force_splits
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

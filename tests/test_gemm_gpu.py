@@ -110,3 +110,17 @@ def test_gemm_dropout_mask_is_reproducible_and_unbiased():
     assert abs(o1.mean().item() - 1.0) < 5e-3   # inverted dropout is unbiased
     vals = o1[o1 != 0]
     assert torch.allclose(vals, torch.full_like(vals, 1 / 0.9), rtol=1e-6)
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(768, 768, 8320, 0), (192, 864, 20000, 0), (304, 520, 4100, 7), (128, 64, 512, 2)])
+def test_gemm_split_k_wgrad(M, N, K, splits):
+    """wgrad shape (both operands MN-major, fp32 accumulate): split-K partial tiles are red.added into the output."""
+    from prismer_b200 import ops
+    dy, x = _mk((K, M), 0.1, seed=11), _mk((K, N), 0.1, seed=12)
+    ref = dy.float().t() @ x.float()
+    acc = torch.full((M, N), 0.5, dtype=torch.float32, device="cuda")
+    ops.gemm(dy, x, trans_a=True, trans_b=True, out=acc, accumulate=True, force_splits=splits)
+    off = torch.full((M, N), 0.5, dtype=torch.float32, device="cuda")
+    ops.gemm(dy, x, trans_a=True, trans_b=True, out=off, accumulate=True, force_splits=1)
+    torch.cuda.synchronize()
+    assert _rel(acc - 0.5, ref) < 5e-5 and _rel(off - 0.5, ref) < 5e-5
