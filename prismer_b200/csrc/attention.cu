@@ -11,6 +11,9 @@
 #include "common.cuh"
 #include "prismer_sm100.h"
 
+#include <mutex>
+#include <unordered_set>
+
 namespace {
 
 constexpr int TQ = 64;      // query rows per CTA (4 warps x 16)
@@ -457,9 +460,15 @@ template <int D> int smem_dkv() { return 4 * 64 * (D + PAD) * 2 + 2 * 64 * 4; }
 
 template <typename K>
 int set_smem(K kern, int bytes) {
-  if (bytes > 48 * 1024) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return PRISMER_ERR_CUDA;
-  }
+  // opt in to > 48 KiB dynamic shared memory once per kernel (keeps stream capture free of attribute calls)
+  static std::mutex mu;
+  static std::unordered_set<const void*> done;
+  if (bytes <= 48 * 1024) return PRISMER_OK;
+  std::lock_guard<std::mutex> lock(mu);
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (done.count(key)) return PRISMER_OK;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return PRISMER_ERR_CUDA;
+  done.insert(key);
   return PRISMER_OK;
 }
 

@@ -19,7 +19,7 @@ namespace {
 constexpr int BM = 128;          // UMMA_M (cta_group::1)
 constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int kNumEpiWarps = 4;
+constexpr int kNumEpiWarps = 8;     // two warps per TMEM lane quarter, each takes every other 32-column chunk
 constexpr int kThreads = 32 * (2 + kNumEpiWarps);
 
 template <int BN> struct Cfg {
@@ -150,6 +150,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;            // which half of the 32-column chunks this warp handles
     int acc = 0; uint32_t acc_phase = 0;
     const bool has_drop = ep.drop_p > 0.f;
     unsigned long long seed = 0;
@@ -163,7 +164,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * 32; c < BN; c += 64) {
         uint32_t raw[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, raw);
         ptx::tmem_ld_wait();
@@ -201,15 +202,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 float z[8]; unpack8(*reinterpret_cast<const bf16x8*>(ap + j), z);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) v[j + t] *= act_bwd(ep.act_grad, z[t]);
+                act_bwd8(ep.act_grad, v + j, z);
               }
             } else {
               _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { v[j] *= act_bwd(ep.act_grad, __bfloat162float(ap[j])); }
             }
           } else if (ep.act) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = act_fwd(ep.act, v[j]);
+            act_fwd32(ep.act, v);
           }
           // ---- dropout on the branch output (before the residual add): roberta.py:138,181
           if (has_drop) {

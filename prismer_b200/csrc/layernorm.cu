@@ -208,7 +208,11 @@ extern "C" int prismer_layernorm_bwd(const void* dy, long long lddy, const void*
   const uint32_t thr16 = static_cast<uint32_t>(drop_p * 65536.0f + 0.5f);
 #define LN_BWD(V)                                                                                                    \
   do {                                                                                                               \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    static int configured_##V = 0;                                                                                   \
+    if (smem > 48 * 1024 && configured_##V < (int)smem) {                                                            \
+      cudaFuncSetAttribute(ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
+      configured_##V = (int)smem;                                                                                    \
+    }                                                                                                                \
     ln_bwd_kernel<V><<<grid, block, smem, stream>>>(                                                                 \
         reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx, mean, rstd, gamma,           \
         reinterpret_cast<const bf16*>(dres), lddres, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dz), \

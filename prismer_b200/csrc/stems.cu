@@ -348,9 +348,11 @@ extern "C" int prismer_resample_bilinear(const float* x, void* out, int B, int C
                                          cudaStream_t stream) {
   if (Wi % 4 || (reinterpret_cast<uintptr_t>(x) & 15)) return PRISMER_ERR_ALIGN;
   const size_t smem = sizeof(float) * 2 * RS_CH * Wi;
-  if (smem > 48 * 1024) {
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && configured < smem) {
     if (cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return PRISMER_ERR_CUDA;
+    configured = smem;
   }
   resample_kernel<<<B * Ho, 256, smem, stream>>>(x, reinterpret_cast<bf16*>(out), B, C, Hi, Wi, Ho, Wo);
   return LAUNCH_CHECK();

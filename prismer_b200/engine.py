@@ -335,7 +335,7 @@ def _pos_for(vit, n_tok: int, save: bool):
     return gemm(W, pos._c16, trans_b=True), W                 # [n_tok, D]
 
 
-def encoder_forward(vit, experts: Dict, save: bool):
+def encoder_forward(vit, experts: Dict, save: bool, inst_table: Optional[torch.Tensor] = None):
     """VisionTransformer.forward (vit.py:133-172).  Returns (out [S*B, D] seq-first rows, S, B, saved)."""
     training = vit.training
     D, p = vit.width, vit.patch_size
@@ -375,7 +375,7 @@ def encoder_forward(vit, experts: Dict, save: bool):
             inst = table = None
             if e == "obj_detection":
                 inst = experts[e]["instance"]
-                table = _instance_table(inst)
+                table = inst_table if inst_table is not None else _instance_table(inst)
             ops.assemble_tokens(t, pos_e, xf[off * B:], D, B * D, B, n_e, D, gh, gw, inst, table,
                                 vit.instance_embedding._c16 if inst is not None else None)
             sv.mods.append(SimpleNamespace(e=e, domain=domain, gh=gh, gw=gw, off=off, n=n_e, inst=inst, table=table, stem=ssv,
@@ -826,24 +826,100 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, anchor, model, experts, input_ids, attention_mask, labels, weights):
         st = _store(model)
         st.refresh()
-        st.seed += 1
-        out, S, B, esv = encoder_forward(model.expert_encoder, experts, save=True)
-        enc = out.view(S, B, -1).transpose(0, 1)
-        _, loss_samples, loss_mean, dsv = decoder_forward(model.text_decoder, input_ids, attention_mask, enc, labels, weights, save=True)
+        loss_mean, esv, dsv = _forward_train(model, experts, input_ids, attention_mask, labels, weights, None)
         ctx.model, ctx.esv, ctx.dsv = model, esv, dsv
         return loss_mean.reshape(())
 
     @staticmethod
     def backward(ctx, g):
         model = ctx.model
-        st = _store(model)
-        st.zero_grad()
-        gs = g.reshape(1).to(F32).contiguous()
-        denc = decoder_backward(model.text_decoder, ctx.dsv, gscale=gs)
-        encoder_backward(model.expert_encoder, ctx.esv, denc)
-        st.publish_grads()
+        _backward_train(model, ctx.esv, ctx.dsv, g.reshape(1).to(F32).contiguous())
+        _store(model).publish_grads()
         ctx.esv = ctx.dsv = None
         return (None,) * 7
+
+
+def _forward_train(model, experts, input_ids, attention_mask, labels, weights, inst_table):
+    st = _store(model)
+    st.seed += 1                                   # new dropout masks every step (device-side counter: graph-replay safe)
+    out, S, B, esv = encoder_forward(model.expert_encoder, experts, save=True, inst_table=inst_table)
+    enc = out.view(S, B, -1).transpose(0, 1)
+    _, _, loss_mean, dsv = decoder_forward(model.text_decoder, input_ids, attention_mask, enc, labels, weights, save=True)
+    return loss_mean, esv, dsv
+
+
+def _backward_train(model, esv, dsv, gscale):
+    st = _store(model)
+    st.zero_grad()
+    denc = decoder_backward(model.text_decoder, dsv, gscale=gscale)
+    encoder_backward(model.expert_encoder, esv, denc)
+
+
+def _canon_experts(experts):
+    return {k: ({kk: vv.contiguous() for kk, vv in v.items()} if isinstance(v, dict) else v.float().contiguous())
+            for k, v in experts.items()}
+
+
+class GraphedTrainStep:
+    """Forward + backward of one training step captured in ONE CUDA graph (static shapes): the ~1200 kernel launches of a
+    step become a single ``cudaGraphLaunch``; dropout masks still change every replay (Philox key lives in device memory
+    and is bumped inside the graph) and the instance-embedding table (vit.py:144-146, host ``random.randint``) is drawn on
+    the host before every replay and copied into a static device buffer.  Gradients land in the flat fp32 buffer."""
+
+    def __init__(self, model, experts, input_ids, attention_mask, labels, weights=None, warmup: int = 2):
+        self.model = model
+        st = self.store = _store(model)
+        st.refresh()
+        dev = st.device
+        self.experts = {k: ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone())
+                        for k, v in _canon_experts(experts).items()}
+        self.ids, self.mask, self.labels = input_ids.clone(), attention_mask.clone(), labels.clone()
+        self.weights = weights.clone() if weights is not None else None
+        self.has_inst = "obj_detection" in self.experts
+        self.table = torch.zeros(256, dtype=torch.int32, device=dev) if self.has_inst else None
+        self.gscale = torch.ones(1, dtype=F32, device=dev)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(warmup):
+                self._draw_table()
+                loss, esv, dsv = _forward_train(model, self.experts, self.ids, self.mask, self.labels, self.weights, self.table)
+                _backward_train(model, esv, dsv, self.gscale)
+                del esv, dsv
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            loss, esv, dsv = _forward_train(model, self.experts, self.ids, self.mask, self.labels, self.weights, self.table)
+            _backward_train(model, esv, dsv, self.gscale)
+            del esv, dsv
+        self.loss = loss
+        st.publish_grads()
+
+    def _draw_table(self):
+        if self.has_inst:
+            self.table.copy_(_instance_table(self.experts["obj_detection"]["instance"]), non_blocking=True)
+
+    def load_inputs(self, experts, input_ids, attention_mask, labels, weights=None, non_blocking=True):
+        """Copy a new batch (host or device tensors) into the graph's static input buffers."""
+        for k, v in experts.items():
+            if isinstance(v, dict):
+                for kk, vv in v.items():
+                    self.experts[k][kk].copy_(vv, non_blocking=non_blocking)
+            else:
+                self.experts[k].copy_(v, non_blocking=non_blocking)
+        self.ids.copy_(input_ids, non_blocking=non_blocking)
+        self.mask.copy_(attention_mask, non_blocking=non_blocking)
+        self.labels.copy_(labels, non_blocking=non_blocking)
+        if weights is not None:
+            self.weights.copy_(weights, non_blocking=non_blocking)
+
+    def __call__(self) -> torch.Tensor:
+        """Replay on the current static inputs; returns the (device, 1-element) batch-mean loss."""
+        self.store.refresh()
+        self._draw_table()
+        self.graph.replay()
+        return self.loss
 
 
 def train_loss(model, experts, input_ids, attention_mask, labels, weights=None) -> torch.Tensor:
