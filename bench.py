@@ -203,6 +203,17 @@ def run_ours(args):
     step(ex_d, ids_d, mask_d)
     torch.cuda.synchronize()
     launches = _C.CALLS - c1
+    # per-entry-point device time of one eager step (CUDA events around every C-ABI call)
+    prof_gemm, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    _C.PROFILE = []
+    step(ex_d, ids_d, mask_d)
+    torch.cuda.synchronize()
+    fam = {}
+    for name, a, b in _C.PROFILE:
+        t = fam.setdefault(name.replace("prismer_", ""), [0, 0.0]); t[0] += 1; t[1] += a.elapsed_time(b)
+    _C.PROFILE = None
+    ops.GEMM_PROFILE = prof_gemm
+    kernel_ms = {k: [v[0], round(v[1], 3)] for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])}
     graphed = graphed_keep
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     if os.environ.get("PRISMER_BENCH_DUMP"):
@@ -241,11 +252,14 @@ def run_ours(args):
         "step_mfu": {"model_gflop_per_img": TRAIN_GFLOP_PER_IMG, "achieved_tflops_per_gpu": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3, 1),
                      "frac_of_peak": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3 / pk["bf16_tflops_sustained"], 4)},
         "host_enqueue_ms_per_step": round(host_ms, 2),
+        "entry_point_ms_per_step": kernel_ms,
         "loss": float(loss),
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_train_baseline(model, sample_batch=2, iters=2)
     print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):

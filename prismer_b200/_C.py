@@ -34,9 +34,37 @@ class GemmArgs(Structure):
 
 
 _lib = None
+PROFILE = None   # set to a list to record (entry point, start_event, end_event) around every C-ABI call (bench.py / tools)
 
 
-def lib() -> ctypes.CDLL:
+class _ProfilingLib:
+    """Proxy used while PROFILE is a list: brackets every C-ABI call with CUDA events on the current stream."""
+
+    def __init__(self, real):
+        self._real = real
+
+    def __getattr__(self, name):
+        fn = getattr(self._real, name)
+        if not name.startswith("prismer_") or name in ("prismer_abi_version", "prismer_check_device"):
+            return fn
+        import torch
+
+        def wrapped(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            PROFILE.append((name, e0, e1))
+            return rc
+        return wrapped
+
+
+def lib():
+    real = _real_lib()
+    return _ProfilingLib(real) if PROFILE is not None else real
+
+
+def _real_lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):

@@ -71,6 +71,22 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, long long rs, 
   }
 }
 
+// Asynchronous variant (cp.async.cg, 16 B, zero-fill for rows >= nvalid): the copy of chunk i+1 overlaps the math of chunk i.
+template <int D>
+__device__ __forceinline__ void load_tile_async(bf16* s, const bf16* g, long long rs, int nvalid) {
+  constexpr int VPR = D / 8;
+  for (int i = threadIdx.x; i < 64 * VPR; i += NWARP * 32) {
+    const int r = i / VPR, c = i % VPR;
+    const bool ok = r < nvalid;
+    const bf16* src = ok ? g + static_cast<long long>(r) * rs + c * 8 : g;
+    const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s + r * (D + PAD) + c * 8));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // A-operand fragments of a 16-row slab (rows r0..r0+15) of a [64, D] smem tile, for k-step kk (16 columns).
 template <int D>
 __device__ __forceinline__ void frag_a(uint32_t (&a)[4], const bf16* s, int r0, int kk, int lane) {
@@ -99,13 +115,21 @@ __device__ __forceinline__ bool key_ok(const AttnParams& p, int b, int qi, int k
 template <int D>
 __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int TILE = 64 * (D + PAD);
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
-  bf16* sK = sQ + 64 * (D + PAD);
-  bf16* sV = sK + 64 * (D + PAD);
+  bf16* sKV = sQ + TILE;                        // [2 stages][K | V]
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qt * TQ;
   const bf16* qg = p.q + b * p.q_bs + static_cast<long long>(q0) * p.q_rs + h * D;
+  int kend = p.Lk;
+  if (p.causal) kend = min(p.Lk, q0 + TQ);
+  const bf16* kbase = p.k + b * p.k_bs + h * D;
+  const bf16* vbase = p.v + b * p.v_bs + h * D;
+  // prologue: chunk 0 in flight while Q is staged
+  load_tile_async<D>(sKV, kbase, p.k_rs, min(TK, p.Lk));
+  load_tile_async<D>(sKV + TILE, vbase, p.v_rs, min(TK, p.Lk));
+  cp_async_commit();
   load_tile<D>(sQ, qg, p.q_rs, min(TQ, p.Lq - q0));
   __syncthreads();
   uint32_t qa[D / 16][4];
@@ -120,14 +144,25 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
   const bool has_drop = p.drop_p > 0.f;
   const Philox philox(has_drop ? *p.seed : 0ull);
   const unsigned long long kgroups = (p.Lk + 7) >> 3;
+  const bool wact = q0 + warp * 16 < p.Lq;      // warps whose 16 query rows are all padding skip the math
 
-  int kend = p.Lk;
-  if (p.causal) kend = min(p.Lk, q0 + TQ);
-  for (int k0 = 0; k0 < kend; k0 += TK) {
+  int stage = 0;
+  for (int k0 = 0; k0 < kend; k0 += TK, stage ^= 1) {
+    const bf16* sK = sKV + stage * 2 * TILE;
+    const bf16* sV = sK + TILE;
+    if (k0 + TK < kend) {                       // prefetch the next chunk into the other stage
+      bf16* nK = sKV + (stage ^ 1) * 2 * TILE;
+      load_tile_async<D>(nK, kbase + static_cast<long long>(k0 + TK) * p.k_rs, p.k_rs, min(TK, p.Lk - k0 - TK));
+      load_tile_async<D>(nK + TILE, vbase + static_cast<long long>(k0 + TK) * p.v_rs, p.v_rs, min(TK, p.Lk - k0 - TK));
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    load_tile<D>(sK, p.k + b * p.k_bs + static_cast<long long>(k0) * p.k_rs + h * D, p.k_rs, min(TK, p.Lk - k0));
-    load_tile<D>(sV, p.v + b * p.v_bs + static_cast<long long>(k0) * p.v_rs + h * D, p.v_rs, min(TK, p.Lk - k0));
-    __syncthreads();
+    int kvalid = min(TK, p.Lk - k0);
+    if (p.causal) kvalid = min(kvalid, q0 + warp * 16 + 16 - k0);
+    if (wact && kvalid > 0) {
     float s[TK / 8][4];
 #pragma unroll
     for (int j = 0; j < TK / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
@@ -135,6 +170,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
     for (int kk = 0; kk < D / 16; ++kk) {
 #pragma unroll
       for (int j2 = 0; j2 < TK / 16; ++j2) {
+        if (j2 * 16 >= kvalid) continue;          // warp-uniform: key columns past Lk (or past the causal frontier)
         uint32_t bk[4];
         frag_b_nk<D>(bk, sK, j2 * 16, kk, lane);
         mma16816(s[2 * j2], qa[kk], bk[0], bk[1]);
@@ -143,15 +179,27 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
     }
     // scale + mask, running max
     float mx[2] = {m[0], m[1]};
+    const bool need_mask = p.causal || p.kmask != nullptr || k0 + TK > p.Lk;   // warp-uniform fast path for interior chunks
+    if (need_mask) {
 #pragma unroll
-    for (int j = 0; j < TK / 8; ++j) {
+      for (int j = 0; j < TK / 8; ++j) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = e >> 1;
-        const int kj = k0 + j * 8 + 2 * t + (e & 1);
-        const float val = key_ok(p, b, row[r], kj) ? s[j][e] * p.scale : -INFINITY;
-        s[j][e] = val;
-        mx[r] = fmaxf(mx[r], val);
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1;
+          const int kj = k0 + j * 8 + 2 * t + (e & 1);
+          const float val = key_ok(p, b, row[r], kj) ? s[j][e] * p.scale : -INFINITY;
+          s[j][e] = val;
+          mx[r] = fmaxf(mx[r], val);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < TK / 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s[j][e] *= p.scale;
+          mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
+        }
       }
     }
 #pragma unroll
@@ -195,6 +243,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
     // O += P V
 #pragma unroll
     for (int kk = 0; kk < TK / 16; ++kk) {
+      if (kk * 16 >= kvalid) continue;
       uint32_t pa[4] = {pack2(s[2 * kk][0], s[2 * kk][1]), pack2(s[2 * kk][2], s[2 * kk][3]),
                         pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
 #pragma unroll
@@ -205,6 +254,8 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
         mma16816(o[2 * n2 + 1], pa, bv[2], bv[3]);
       }
     }
+    }  // wact
+    __syncthreads();   // every warp is done with this stage before the next iteration's prefetch may overwrite it
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -230,17 +281,25 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
 template <int D>
 __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int TILE = 64 * (D + PAD);
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
-  bf16* sdO = sQ + 64 * (D + PAD);
-  bf16* sK = sdO + 64 * (D + PAD);
-  bf16* sV = sK + 64 * (D + PAD);
+  bf16* sdO = sQ + TILE;
+  bf16* sKV = sdO + TILE;                       // [2 stages][K | V]
+  bf16* sO = sKV + 2 * TILE;                    // O is staged in stage 1's K slot during the prologue
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qt * TQ;
   const int nq = min(TQ, p.Lq - q0);
+  int kend = p.Lk;
+  if (p.causal) kend = min(p.Lk, q0 + TQ);
+  const bf16* kbase = p.k + b * p.k_bs + h * D;
+  const bf16* vbase = p.v + b * p.v_bs + h * D;
+  load_tile_async<D>(sKV, kbase, p.k_rs, min(TK, p.Lk));
+  load_tile_async<D>(sKV + TILE, vbase, p.v_rs, min(TK, p.Lk));
+  cp_async_commit();
   load_tile<D>(sQ, p.q + b * p.q_bs + static_cast<long long>(q0) * p.q_rs + h * D, p.q_rs, nq);
   load_tile<D>(sdO, p.dout + b * p.do_bs + static_cast<long long>(q0) * p.do_rs + h * D, p.do_rs, nq);
-  load_tile<D>(sK, p.o + b * p.o_bs + static_cast<long long>(q0) * p.o_rs + h * D, p.o_rs, nq);  // O staged in sK
+  load_tile<D>(sO, p.o + b * p.o_bs + static_cast<long long>(q0) * p.o_rs + h * D, p.o_rs, nq);
   __syncthreads();
   // delta = rowsum(dO * O): each warp its 16 rows, 2 lanes per row
   const long long bh = static_cast<long long>(b) * p.H + h;
@@ -248,7 +307,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
     const int r = warp * 16 + (lane >> 1);
     float acc = 0.f;
     for (int c = (lane & 1) * (D / 2); c < ((lane & 1) + 1) * (D / 2); ++c)
-      acc += __bfloat162float(sdO[r * (D + PAD) + c]) * __bfloat162float(sK[r * (D + PAD) + c]);
+      acc += __bfloat162float(sdO[r * (D + PAD) + c]) * __bfloat162float(sO[r * (D + PAD) + c]);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     if ((lane & 1) == 0 && q0 + r < p.Lq) p.delta[bh * p.Lq + q0 + r] = acc;
   }
@@ -267,14 +326,25 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
   const bool has_drop = p.drop_p > 0.f;
   const Philox philox(has_drop ? *p.seed : 0ull);
   const unsigned long long kgroups = (p.Lk + 7) >> 3;
+  const bool wact = q0 + warp * 16 < p.Lq;
 
-  int kend = p.Lk;
-  if (p.causal) kend = min(p.Lk, q0 + TQ);
-  for (int k0 = 0; k0 < kend; k0 += TK) {
+  int stage = 0;
+  for (int k0 = 0; k0 < kend; k0 += TK, stage ^= 1) {
+    const bf16* sK = sKV + stage * 2 * TILE;
+    const bf16* sV = sK + TILE;
+    if (k0 + TK < kend) {
+      bf16* nK = sKV + (stage ^ 1) * 2 * TILE;
+      load_tile_async<D>(nK, kbase + static_cast<long long>(k0 + TK) * p.k_rs, p.k_rs, min(TK, p.Lk - k0 - TK));
+      load_tile_async<D>(nK + TILE, vbase + static_cast<long long>(k0 + TK) * p.v_rs, p.v_rs, min(TK, p.Lk - k0 - TK));
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    load_tile<D>(sK, p.k + b * p.k_bs + static_cast<long long>(k0) * p.k_rs + h * D, p.k_rs, min(TK, p.Lk - k0));
-    load_tile<D>(sV, p.v + b * p.v_bs + static_cast<long long>(k0) * p.v_rs + h * D, p.v_rs, min(TK, p.Lk - k0));
-    __syncthreads();
+    int kvalid = min(TK, p.Lk - k0);
+    if (p.causal) kvalid = min(kvalid, q0 + warp * 16 + 16 - k0);
+    if (wact && kvalid > 0) {
     float s[TK / 8][4], dp[TK / 8][4];
 #pragma unroll
     for (int j = 0; j < TK / 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
@@ -285,6 +355,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
       frag_a<D>(doa, sdO, warp * 16, kk, lane);
 #pragma unroll
       for (int j2 = 0; j2 < TK / 16; ++j2) {
+        if (j2 * 16 >= kvalid) continue;
         uint32_t bk[4], bv[4];
         frag_b_nk<D>(bk, sK, j2 * 16, kk, lane);
         mma16816(s[2 * j2], qa, bk[0], bk[1]);
@@ -317,6 +388,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
     // dQ += dS K   (B operand: K tile is [key k][d n] -> n contiguous -> transposed ldmatrix)
 #pragma unroll
     for (int kk = 0; kk < TK / 16; ++kk) {
+      if (kk * 16 >= kvalid) continue;
       uint32_t pa[4] = {pack2(s[2 * kk][0], s[2 * kk][1]), pack2(s[2 * kk][2], s[2 * kk][3]),
                         pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
 #pragma unroll
@@ -327,6 +399,8 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
         mma16816(dq[2 * n2 + 1], pa, bk[2], bk[3]);
       }
     }
+    }  // wact
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -343,12 +417,11 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
 template <int D>
 __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int TILE = 64 * (D + PAD);
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);
-  bf16* sV = sK + 64 * (D + PAD);
-  bf16* sQ = sV + 64 * (D + PAD);
-  bf16* sdO = sQ + 64 * (D + PAD);
-  float* sLse = reinterpret_cast<float*>(sdO + 64 * (D + PAD));
-  float* sDl = sLse + 64;
+  bf16* sV = sK + TILE;
+  bf16* sQdO = sV + TILE;                       // [2 stages][Q | dO]
+  float* sStat = reinterpret_cast<float*>(sQdO + 4 * TILE);   // [2 stages][lse(64) | delta(64)]
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int k0 = kt * TK;
@@ -368,20 +441,38 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(AttnParams p) 
   const bool has_drop = p.drop_p > 0.f;
   const Philox philox(has_drop ? *p.seed : 0ull);
   const unsigned long long kgroups = (p.Lk + 7) >> 3;
+  const bool kact = k0 + warp * 16 < p.Lk;     // warps whose 16 keys are all padding skip the math
 
   const int qstart = p.causal ? (k0 / TQ) * TQ : 0;
-  for (int q0 = qstart; q0 < p.Lq; q0 += TQ) {
+  auto prefetch = [&](int q0, int st) {
     const int nq = min(TQ, p.Lq - q0);
-    __syncthreads();
-    load_tile<D>(sQ, p.q + b * p.q_bs + static_cast<long long>(q0) * p.q_rs + h * D, p.q_rs, nq);
-    load_tile<D>(sdO, p.dout + b * p.do_bs + static_cast<long long>(q0) * p.do_rs + h * D, p.do_rs, nq);
+    bf16* dQ = sQdO + st * 2 * TILE;
+    load_tile_async<D>(dQ, p.q + b * p.q_bs + static_cast<long long>(q0) * p.q_rs + h * D, p.q_rs, nq);
+    load_tile_async<D>(dQ + TILE, p.dout + b * p.do_bs + static_cast<long long>(q0) * p.do_rs + h * D, p.do_rs, nq);
+    cp_async_commit();
     if (threadIdx.x < 64) {
       const bool ok = threadIdx.x < nq;
-      sLse[threadIdx.x] = ok ? p.lse[bh * p.Lq + q0 + threadIdx.x] : 0.f;
-      sDl[threadIdx.x] = ok ? p.delta[bh * p.Lq + q0 + threadIdx.x] : 0.f;
+      sStat[st * 128 + threadIdx.x] = ok ? p.lse[bh * p.Lq + q0 + threadIdx.x] : 0.f;
+      sStat[st * 128 + 64 + threadIdx.x] = ok ? p.delta[bh * p.Lq + q0 + threadIdx.x] : 0.f;
+    }
+  };
+  prefetch(qstart, 0);
+  int stage = 0;
+  for (int q0 = qstart; q0 < p.Lq; q0 += TQ, stage ^= 1) {
+    const bf16* sQ = sQdO + stage * 2 * TILE;
+    const bf16* sdO = sQ + TILE;
+    const float* sLse = sStat + stage * 128;
+    const float* sDl = sLse + 64;
+    if (q0 + TQ < p.Lq) {
+      prefetch(q0 + TQ, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     // S^T = K Q^T (16 keys x 64 queries per warp), dP^T = V dO^T
+    const int nqv = min(TQ, p.Lq - q0);
+    if (kact) {
     float s[TQ / 8][4], dp[TQ / 8][4];
 #pragma unroll
     for (int j = 0; j < TQ / 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
@@ -392,6 +483,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(AttnParams p) 
       frag_a<D>(va, sV, warp * 16, kk, lane);
 #pragma unroll
       for (int j2 = 0; j2 < TQ / 16; ++j2) {
+        if (j2 * 16 >= nqv) continue;               // query columns past Lq
         uint32_t bq[4], bo[4];
         frag_b_nk<D>(bq, sQ, j2 * 16, kk, lane);
         mma16816(s[2 * j2], ka, bq[0], bq[1]);
@@ -424,6 +516,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(AttnParams p) 
     // dV += Pd^T dO ; dK += dS^T Q    (B operands [k = query][n = d]: n contiguous -> transposed ldmatrix)
 #pragma unroll
     for (int kk = 0; kk < TQ / 16; ++kk) {
+      if (kk * 16 >= nqv) continue;
       uint32_t pa[4] = {pack2(pd[2 * kk][0], pd[2 * kk][1]), pack2(pd[2 * kk][2], pd[2 * kk][3]),
                         pack2(pd[2 * kk + 1][0], pd[2 * kk + 1][1]), pack2(pd[2 * kk + 1][2], pd[2 * kk + 1][3])};
       uint32_t sa[4] = {pack2(s[2 * kk][0], s[2 * kk][1]), pack2(s[2 * kk][2], s[2 * kk][3]),
@@ -439,6 +532,8 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(AttnParams p) 
         mma16816(dk[2 * n2 + 1], sa, bq[2], bq[3]);
       }
     }
+    }  // kact
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -454,9 +549,213 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(AttnParams p) 
   }
 }
 
-template <int D> int smem_fwd() { return 3 * 64 * (D + PAD) * 2; }
-template <int D> int smem_dq() { return 4 * 64 * (D + PAD) * 2; }
-template <int D> int smem_dkv() { return 4 * 64 * (D + PAD) * 2 + 2 * 64 * 4; }
+
+// ------------------------------------------------------------------------------------------------ backward, Lq <= 64 fused
+// One CTA per (b, h) when all queries fit one tile (resampler: 64 latents; decoder: T <= 45): S, P, dP, dS are computed ONCE
+// per key chunk; dQ accumulates in registers over the chunks, and since every query is in this CTA, dK/dV of a chunk are
+// complete after that chunk and are written straight out (5 matrix products per chunk instead of 7 over two kernels, half the
+// loads, half the dropout RNG, one launch).  P^T / dS^T reach the second pair of products through shared memory.
+template <int D>
+__device__ __forceinline__ void frag_a_t(uint32_t (&a)[4], const bf16* s, int m0, int k0, int lane, int ld) {
+  // A[m][k] fragment (16x16) from a tile stored [k][m] (m contiguous): transposed ldmatrix
+  ldsm_x4_t(a, s + (k0 + (lane & 7) + ((lane >> 4) & 1) * 8) * ld + m0 + ((lane >> 3) & 1) * 8);
+}
+
+template <int D>
+__global__ void __launch_bounds__(NWARP * 32) attn_bwd_fused_kernel(AttnParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int TILE = 64 * (D + PAD);
+  constexpr int PLD = TK + PAD;
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sdO = sQ + TILE;
+  bf16* sKV = sdO + TILE;                       // [2 stages][K | V]
+  bf16* sP = sKV + 4 * TILE;                    // [64 q][TK keys] dropped probabilities
+  bf16* sdS = sP + 64 * PLD;                    // [64 q][TK keys] score gradients
+  float* sDelta = reinterpret_cast<float*>(sdS + 64 * PLD);
+  bf16* sO = sKV + 2 * TILE;                    // prologue only (stage 1's K slot)
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nq = p.Lq;                          // <= 64
+  const long long bh = static_cast<long long>(b) * p.H + h;
+  const bf16* kbase = p.k + b * p.k_bs + h * D;
+  const bf16* vbase = p.v + b * p.v_bs + h * D;
+  load_tile_async<D>(sKV, kbase, p.k_rs, min(TK, p.Lk));
+  load_tile_async<D>(sKV + TILE, vbase, p.v_rs, min(TK, p.Lk));
+  cp_async_commit();
+  load_tile<D>(sQ, p.q + b * p.q_bs + h * D, p.q_rs, nq);
+  load_tile<D>(sdO, p.dout + b * p.do_bs + h * D, p.do_rs, nq);
+  load_tile<D>(sO, p.o + b * p.o_bs + h * D, p.o_rs, nq);
+  __syncthreads();
+  {
+    const int r = warp * 16 + (lane >> 1);
+    float acc = 0.f;
+    for (int c = (lane & 1) * (D / 2); c < ((lane & 1) + 1) * (D / 2); ++c)
+      acc += __bfloat162float(sdO[r * (D + PAD) + c]) * __bfloat162float(sO[r * (D + PAD) + c]);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if ((lane & 1) == 0) sDelta[r] = acc;
+  }
+  __syncthreads();
+  const int row[2] = {warp * 16 + g, warp * 16 + g + 8};
+  float lse[2], dl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lse[r] = row[r] < nq ? p.lse[bh * p.Lq + row[r]] : 0.f;
+    dl[r] = sDelta[row[r]];
+  }
+  float dq[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  const bool has_drop = p.drop_p > 0.f;
+  const Philox philox(has_drop ? *p.seed : 0ull);
+  const unsigned long long kgroups = (p.Lk + 7) >> 3;
+  const bool wact = warp * 16 < nq;
+  const int kend = p.causal ? min(p.Lk, TQ) : p.Lk;
+
+  int stage = 0;
+  for (int k0 = 0; k0 < kend; k0 += TK, stage ^= 1) {
+    const bf16* sK = sKV + stage * 2 * TILE;
+    const bf16* sV = sK + TILE;
+    if (k0 + TK < kend) {
+      bf16* nK = sKV + (stage ^ 1) * 2 * TILE;
+      load_tile_async<D>(nK, kbase + static_cast<long long>(k0 + TK) * p.k_rs, p.k_rs, min(TK, p.Lk - k0 - TK));
+      load_tile_async<D>(nK + TILE, vbase + static_cast<long long>(k0 + TK) * p.v_rs, p.v_rs, min(TK, p.Lk - k0 - TK));
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int kvalid = min(TK, p.Lk - k0);
+    // ---- phase A: this warp's 16 query rows x the chunk's keys
+    {
+      float s[TK / 8][4], dp[TK / 8][4];
+#pragma unroll
+      for (int j = 0; j < TK / 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+      if (wact) {
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          uint32_t qa[4], doa[4];
+          frag_a<D>(qa, sQ, warp * 16, kk, lane);
+          frag_a<D>(doa, sdO, warp * 16, kk, lane);
+#pragma unroll
+          for (int j2 = 0; j2 < TK / 16; ++j2) {
+            if (j2 * 16 >= kvalid) continue;
+            uint32_t bk[4], bv[4];
+            frag_b_nk<D>(bk, sK, j2 * 16, kk, lane);
+            mma16816(s[2 * j2], qa, bk[0], bk[1]);
+            mma16816(s[2 * j2 + 1], qa, bk[2], bk[3]);
+            frag_b_nk<D>(bv, sV, j2 * 16, kk, lane);
+            mma16816(dp[2 * j2], doa, bv[0], bv[1]);
+            mma16816(dp[2 * j2 + 1], doa, bv[2], bv[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < TK / 8; ++j) {
+        uint32_t keep[2] = {0xffffffffu, 0xffffffffu};
+        if (has_drop && wact) {
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+            keep[r] = dropout_keep8(philox, (bh * p.Lq + row[r]) * kgroups + ((k0 >> 3) + j), p.rng_stream, p.thr16);
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float pdv[2], dsv[2];
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int e = 2 * r + c2;
+            const int kj = k0 + j * 8 + 2 * t + c2;
+            float pv = 0.f;
+            if (wact && row[r] < nq && key_ok(p, b, row[r], kj)) pv = __expf(s[j][e] * p.scale - lse[r]);
+            float keepf = 1.f;
+            if (has_drop) keepf = ((keep[r] >> (2 * t + c2)) & 1u) ? p.drop_scale : 0.f;
+            pdv[c2] = pv * keepf;
+            dsv[c2] = pv * (dp[j][e] * keepf - dl[r]) * p.scale;
+            s[j][e] = dsv[c2];
+          }
+          *reinterpret_cast<__nv_bfloat162*>(sP + row[r] * PLD + j * 8 + 2 * t) = __floats2bfloat162_rn(pdv[0], pdv[1]);
+          *reinterpret_cast<__nv_bfloat162*>(sdS + row[r] * PLD + j * 8 + 2 * t) = __floats2bfloat162_rn(dsv[0], dsv[1]);
+        }
+      }
+      if (wact) {   // dQ += dS K
+#pragma unroll
+        for (int kk = 0; kk < TK / 16; ++kk) {
+          if (kk * 16 >= kvalid) continue;
+          uint32_t pa[4] = {pack2(s[2 * kk][0], s[2 * kk][1]), pack2(s[2 * kk][2], s[2 * kk][3]),
+                            pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+#pragma unroll
+          for (int n2 = 0; n2 < D / 16; ++n2) {
+            uint32_t bk[4];
+            frag_b_kn<D>(bk, sK, kk * 16, n2 * 16, lane);
+            mma16816(dq[2 * n2], pa, bk[0], bk[1]);
+            mma16816(dq[2 * n2 + 1], pa, bk[2], bk[3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase B: this warp's 16 keys of the chunk: dV = P^T dO, dK = dS^T Q (reduction over all queries of the CTA)
+    if (warp * 16 < kvalid) {
+      float dk[D / 8][4], dv[D / 8][4];
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < TQ / 16; ++kk) {
+        if (kk * 16 >= nq) continue;
+        uint32_t pa[4], sa[4];
+        frag_a_t<D>(pa, sP, warp * 16, kk * 16, lane, PLD);
+        frag_a_t<D>(sa, sdS, warp * 16, kk * 16, lane, PLD);
+#pragma unroll
+        for (int n2 = 0; n2 < D / 16; ++n2) {
+          uint32_t bo[4], bq[4];
+          frag_b_kn<D>(bo, sdO, kk * 16, n2 * 16, lane);
+          mma16816(dv[2 * n2], pa, bo[0], bo[1]);
+          mma16816(dv[2 * n2 + 1], pa, bo[2], bo[3]);
+          frag_b_kn<D>(bq, sQ, kk * 16, n2 * 16, lane);
+          mma16816(dk[2 * n2], sa, bq[0], bq[1]);
+          mma16816(dk[2 * n2 + 1], sa, bq[2], bq[3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int key = k0 + warp * 16 + g + 8 * r;
+        if (key < p.Lk) {
+          bf16* kg = p.dk + b * p.dk_bs + static_cast<long long>(key) * p.dk_rs + h * D;
+          bf16* vg = p.dv + b * p.dv_bs + static_cast<long long>(key) * p.dv_rs + h * D;
+#pragma unroll
+          for (int i = 0; i < D / 8; ++i) {
+            *reinterpret_cast<__nv_bfloat162*>(kg + i * 8 + 2 * t) = __floats2bfloat162_rn(dk[i][2 * r], dk[i][2 * r + 1]);
+            *reinterpret_cast<__nv_bfloat162*>(vg + i * 8 + 2 * t) = __floats2bfloat162_rn(dv[i][2 * r], dv[i][2 * r + 1]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // keys of chunks that were never visited (causal: none beyond the tile) need zero gradients
+  if (p.causal && kend < p.Lk) {
+    for (int key = kend + warp; key < p.Lk; key += NWARP)
+      for (int c = lane; c < D; c += 32) {
+        p.dk[b * p.dk_bs + static_cast<long long>(key) * p.dk_rs + h * D + c] = __float2bfloat16(0.f);
+        p.dv[b * p.dv_bs + static_cast<long long>(key) * p.dv_rs + h * D + c] = __float2bfloat16(0.f);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (row[r] < nq) {
+      bf16* dg = p.dq + b * p.dq_bs + static_cast<long long>(row[r]) * p.dq_rs + h * D;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i)
+        *reinterpret_cast<__nv_bfloat162*>(dg + i * 8 + 2 * t) = __floats2bfloat162_rn(dq[i][2 * r], dq[i][2 * r + 1]);
+    }
+  }
+}
+
+template <int D> int smem_fused() { return 6 * 64 * (D + PAD) * 2 + 2 * 64 * (TK + PAD) * 2 + 64 * 4; }
+
+template <int D> int smem_fwd() { return 5 * 64 * (D + PAD) * 2; }
+template <int D> int smem_dq() { return 6 * 64 * (D + PAD) * 2; }
+template <int D> int smem_dkv() { return 6 * 64 * (D + PAD) * 2 + 4 * 64 * 4; }
 
 template <typename K>
 int set_smem(K kern, int bytes) {
@@ -516,6 +815,15 @@ extern "C" int prismer_attention_bwd(const PrismerAttnArgs* a, cudaStream_t stre
   if (!p.dout || !p.dq || !p.dk || !p.dv || !p.delta || !p.lse) return PRISMER_ERR_SHAPE;
   const long long strides[] = {a->do_bs, a->do_rs, a->dq_bs, a->dq_rs, a->dk_bs, a->dk_rs, a->dv_bs, a->dv_rs};
   for (long long s : strides) if (s % 8) return PRISMER_ERR_ALIGN;
+  if (p.Lq <= TQ) {   // all queries in one tile: fused single-kernel backward
+    dim3 gf(1, p.H, p.B);
+#define BWDF(D_)                                                                                 \
+  { rc = set_smem(attn_bwd_fused_kernel<D_>, smem_fused<D_>()); if (rc) return rc;               \
+    attn_bwd_fused_kernel<D_><<<gf, NWARP * 32, smem_fused<D_>(), stream>>>(p); }
+    switch (a->d) { case 32: BWDF(32) break; case 64: BWDF(64) break; case 96: BWDF(96) break; default: BWDF(128) break; }
+#undef BWDF
+    return LAUNCH_CHECK();
+  }
   dim3 gq((p.Lq + TQ - 1) / TQ, p.H, p.B), gk((p.Lk + TK - 1) / TK, p.H, p.B);
 #define BWD(D_)                                                                                  \
   { rc = set_smem(attn_bwd_dq_kernel<D_>, smem_dq<D_>()); if (rc) return rc;                     \

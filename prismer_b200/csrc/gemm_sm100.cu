@@ -28,7 +28,8 @@ template <int BN> struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages (power of two >= 32 for BN in {64,128,256})
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = kNumEpiWarps * 4096;   // per-epilogue-warp 32x32 staging tile (coalesced stores)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
 
 struct EpiParams {
@@ -56,6 +57,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = empty_bar + C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* staging = smem + C::kStages * C::kStageBytes + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -156,6 +158,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     unsigned long long seed = 0;
     if (has_drop) seed = *ep.seed;
     const Philox philox(seed);
+    uint8_t* stg = staging + (warp - 2) * 4096;
+    // Coalesced stores of a 32x32 chunk: every lane parks its row in a swizzled (bank-conflict-free) smem tile, then the warp
+    // writes it back with each instruction covering whole rows segments (bf16: 8 rows x 64 B, fp32: 4 rows x 128 B) -- full
+    // 32-byte sectors instead of 32 row-strided 16-byte pieces per instruction.
+    auto store_bf16_staged = [&](bf16* blk, long long ld, const float* v, int rows_valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pack8(v + 8 * j);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i, ch = lane & 3;
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+        if (rr < rows_valid) *reinterpret_cast<uint4*>(blk + rr * ld + ch * 8) = val;
+      }
+      __syncwarp();
+    };
+    auto store_f32_staged = [&](float* blk, long long ld, const float* v, int rows_valid, int mode /*0 store, 1 accumulate, 2 atomic*/) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = (lane >> 3) + 4 * i, ch = lane & 7;
+        float4 val = *reinterpret_cast<const float4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+        if (rr < rows_valid) {
+          float4* dst = reinterpret_cast<float4*>(blk + rr * ld + ch * 4);
+          if (mode == 2) {
+            atomicAdd(dst, val);
+          } else {
+            if (mode == 1) { const float4 p = *dst; val.x += p.x; val.y += p.y; val.z += p.z; val.w += p.w; }
+            *dst = val;
+          }
+        }
+      }
+      __syncwarp();
+    };
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int tile = w % num_tiles;
       const int m0 = (tile / num_n) * BM, n0 = (tile % num_n) * BN;
@@ -163,17 +203,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < M;
+      const int rows_valid = min(32, M - (m0 + q * 32));   // rows of this warp's 32-row slab that exist (may be <= 0)
 #pragma unroll 1
       for (int c = chalf * 32; c < BN; c += 64) {
         uint32_t raw[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, raw);
         ptx::tmem_ld_wait();
         const int col0 = n0 + c;
-        if (row_ok && col0 < N) {
-          float v[32];
+        if (col0 >= N || rows_valid <= 0) continue;          // warp-uniform
+        const bool full = (col0 + 32 <= N);                  // warp-uniform
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * ep.alpha;
-          const bool full = (col0 + 32 <= N);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * ep.alpha;
+        if (row_ok) {
           // ---- bias
           if (ep.bias) {
             if (full) {
@@ -187,15 +229,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           // ---- aux: save pre-activation / multiply by the activation derivative
-          if (ep.aux_out) {
+          if (ep.aux_out && !full) {
             bf16* ap = ep.aux_out + static_cast<long long>(row) * ep.ldaux + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(ap + j) = pack8(v + j);
-            } else {
-              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { ap[j] = __float2bfloat16(v[j]); }
-            }
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { ap[j] = __float2bfloat16(v[j]); }
           }
+        }
+        if (ep.aux_out && full)      // pre-activation saved for the backward (all lanes participate in the staged store)
+          store_bf16_staged(ep.aux_out + static_cast<long long>(m0 + q * 32) * ep.ldaux + col0, ep.ldaux, v, rows_valid);
+        if (row_ok) {
           if (ep.act_grad) {
             const bf16* ap = ep.aux_in + static_cast<long long>(row) * ep.ldaux + col0;
             if (full) {
@@ -234,35 +275,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { v[j] += __bfloat162float(rp[j]); }
             }
           }
-          // ---- store
+        }
+        // ---- store
+        if (full) {
+          if (ep.out_fp32)
+            store_f32_staged(reinterpret_cast<float*>(ep.C) + static_cast<long long>(m0 + q * 32) * ep.ldc + col0, ep.ldc, v, rows_valid,
+                             splits > 1 ? 2 : (ep.accumulate ? 1 : 0));
+          else
+            store_bf16_staged(reinterpret_cast<bf16*>(ep.C) + static_cast<long long>(m0 + q * 32) * ep.ldc + col0, ep.ldc, v, rows_valid);
+        } else if (row_ok) {                                  // N tail: per-element path
           if (ep.out_fp32) {
             float* cp = reinterpret_cast<float*>(ep.C) + static_cast<long long>(row) * ep.ldc + col0;
-            if (splits > 1) {   // partial tile of a split-K work item: vector reduction into the fp32 output
-              if (full) {
+            if (splits > 1) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(cp + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (col0 + j < N) atomicAdd(cp + j, v[j]);
-              }
-            } else if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (ep.accumulate) { float4 p = *reinterpret_cast<float4*>(cp + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-                *reinterpret_cast<float4*>(cp + j) = o;
-              }
+              for (int j = 0; j < 32; ++j) if (col0 + j < N) atomicAdd(cp + j, v[j]);
             } else {
               _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { cp[j] = ep.accumulate ? cp[j] + v[j] : v[j]; }
             }
           } else {
             bf16* cp = reinterpret_cast<bf16*>(ep.C) + static_cast<long long>(row) * ep.ldc + col0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) *reinterpret_cast<bf16x8*>(cp + j) = pack8(v + j);
-            } else {
-              _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { cp[j] = __float2bfloat16(v[j]); }
-            }
+            _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { cp[j] = __float2bfloat16(v[j]); }
           }
         }
       }

@@ -220,19 +220,30 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_gather_kernel(const bf16* __r
     for (long long pix = static_cast<long long>(blockIdx.x) * lanes + rl; pix < npix; pix += static_cast<long long>(gridDim.x) * lanes) {
       const int xi = static_cast<int>(pix % W), yi = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
       float da[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int kh = 0; kh < ksz; ++kh) {
-        const int ty = yi + pad - kh;
-        if (ty < 0 || ty % stride) continue;
-        const int yo = ty / stride;
-        if (yo >= Ho) continue;
-        for (int kw = 0; kw < ksz; ++kw) {
-          const int tx = xi + pad - kw;
-          if (tx < 0 || tx % stride) continue;
-          const int xo = tx / stride;
-          if (xo >= Wo) continue;
+      // all (<= 9) tap loads are issued before any is consumed: 9 independent 128-bit loads in flight per thread
+      bf16x8 taps_v[9];
+      bool taps_ok[9];
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) {
+        const int kh = tp / 3, kw = tp % 3;
+        bool ok = tp < taps && kh < ksz && kw < ksz;
+        const int ty = yi + pad - (ksz == 3 ? kh : 0), tx = xi + pad - (ksz == 3 ? kw : 0);
+        ok = ok && (ksz == 3 || tp == 0) && ty >= 0 && tx >= 0 && (ty % stride) == 0 && (tx % stride) == 0;
+        const int yo = ty / stride, xo = tx / stride;
+        ok = ok && yo < Ho && xo < Wo;
+        taps_ok[tp] = ok;
+        taps_v[tp] = make_uint4(0, 0, 0, 0);
+        if (ok) {
+          const int tapi = ksz == 3 ? tp : 0;
+          taps_v[tp] = *reinterpret_cast<const bf16x8*>(dAcol + ((static_cast<long long>(b) * Ho + yo) * Wo + xo) * (static_cast<long long>(taps) * C) +
+                                                        tapi * C + cvi * 8);
+        }
+      }
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) {
+        if (taps_ok[tp]) {
           float f[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(dAcol + ((static_cast<long long>(b) * Ho + yo) * Wo + xo) * (static_cast<long long>(taps) * C) +
-                                                   (kh * ksz + kw) * C + cvi * 8), f);
+          unpack8(taps_v[tp], f);
 #pragma unroll
           for (int t = 0; t < 8; ++t) da[t] += f[t];
         }
@@ -402,7 +413,7 @@ extern "C" int prismer_bn_relu_bwd(const void* dAcol, const void* y, const float
   const long long M = static_cast<long long>(B) * H * W;
   const int lanes = 256 / (C / 8);
   long long blocks = (M + lanes - 1) / lanes;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   bn_relu_bwd_gather_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
       reinterpret_cast<const bf16*>(dAcol), reinterpret_cast<const bf16*>(y), scale, shift, mean, rstd,
       reinterpret_cast<bf16*>(dn_scratch), red, B, H, W, C, ksz, stride, Ho, Wo);

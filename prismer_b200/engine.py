@@ -204,15 +204,70 @@ def _ln_bwd(dy, x, mean, rstd, ln, dres=None, dz=False, drop_p=0.0, seed=None, s
                              rng_stream=stream)
 
 
+class _SideStream:
+    """Weight / bias gradients are off the backward's critical path (only the dgrad chain feeds the next layer), so they are
+    enqueued on a second stream: under the CUDA graph they become parallel branches that fill the SMs the small decoder
+    dgrad GEMMs (M = B*T = 960 rows) leave idle.  Inputs are kept alive until the join at the end of the backward."""
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.keep = []
+        self.active = False
+
+    def run(self, fn, *tensors):
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            fn()
+        self.keep.extend(tensors)
+        self.active = True
+
+    def join(self):
+        if self.active:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.active = False
+        self.keep.clear()
+
+
+SIDE_STREAM = True
+_sides = {}
+
+
+def _side(t) -> Optional[_SideStream]:
+    if not SIDE_STREAM:
+        return None
+    dev = t.device
+    sd = _sides.get(dev)
+    if sd is None:
+        sd = _sides[dev] = _SideStream(dev)
+    return sd
+
+
+def _side_join(device):
+    sd = _sides.get(device)
+    if sd is not None:
+        sd.join()
+
+
+def _off_critical_path(fn, *tensors):
+    sd = _side(tensors[0])
+    if sd is None:
+        fn()
+    else:
+        sd.run(fn, *tensors)
+
+
 def _wgrad(dy2d, x2d, wg):
     """wg[N_out, K_in] (fp32) += dy^T . x   (both operands MN-major: no transposes materialised)."""
     if wg is not None:
-        gemm(dy2d, x2d, trans_a=True, trans_b=True, out=wg, accumulate=True)
+        _off_critical_path(lambda: gemm(dy2d, x2d, trans_a=True, trans_b=True, out=wg, accumulate=True), dy2d, x2d)
 
 
 def _bgrad(dy2d, bg):
     if bg is not None:
-        ops.colsum(dy2d, bg)
+        _off_critical_path(lambda: ops.colsum(dy2d, bg), dy2d)
 
 
 def _lin_grads(dy2d, x2d, lin: nn.Linear):
@@ -298,9 +353,12 @@ def _stem_bwd(stem, sv, dtok):
             L.dy, L.dA = dy, dA
         if conv.weight.requires_grad:
             wp = conv.weight._pack16
-            dwp = torch.zeros(wp.shape, dtype=F32, device=dy.device)
-            gemm(dy, L.A, trans_a=True, trans_b=True, out=dwp, accumulate=True)    # accumulate => split-K eligible (K = B*Ho*Wo)
-            ops.conv_weight_unpack_grad(dwp, conv.weight._g32)
+            def _conv_wgrad(dy=dy, A=L.A, wp=wp, g=conv.weight._g32):
+                dwp = torch.zeros(wp.shape, dtype=F32, device=dy.device)
+                gemm(dy, A, trans_a=True, trans_b=True, out=dwp, accumulate=True)    # accumulate => split-K eligible (K = B*Ho*Wo)
+                ops.conv_weight_unpack_grad(dwp, g)
+                _sides[dy.device].keep.append(dwp) if dy.device in _sides else None
+            _off_critical_path(_conv_wgrad, dy, L.A)
         if i > 0:
             dA = gemm(dy, conv.weight._pack16, trans_b=True)   # [M_i, 9*C_{i-1}] in (kh,kw,c) order
             ksz, s_next, Ho, Wo = 3, L.s, L.Ho, L.Wo
@@ -583,8 +641,19 @@ def _x3(t2d, B, S, bs_rows, rs_rows, c0, c1):
     return torch.as_strided(t2d, (B, S, c1 - c0), (bs_rows * ld, rs_rows * ld, 1), t2d.storage_offset() + c0)
 
 
-def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: bool, need_logits: bool = True):
-    """RobertaForCausalLMModified.forward (roberta.py:358-399) on a batch of pre-tokenised ids."""
+def cross_kv(dec, enc):
+    """All decoder layers' cross-attention K/V projections of the visual tokens in ONE grouped GEMM
+    ([S*B, Dv] x [Dv, L*2H]); generation computes it once per call instead of once per step and layer (roberta.py:103)."""
+    _store(dec)
+    enc_flat, B, S, ebs, ers_ = _enc_layout(enc)
+    xg = dec.roberta.encoder._grp
+    return SimpleNamespace(enc_flat=enc_flat, kv_all=gemm(enc_flat, xg.w16, bias=xg.b), B=B, S=S, bs=ebs, rs=ers_)
+
+
+def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: bool, need_logits: bool = True,
+                    kv: Optional[SimpleNamespace] = None, last_only: bool = False):
+    """RobertaForCausalLMModified.forward (roberta.py:358-399) on a batch of pre-tokenised ids.
+    ``kv``: precomputed ``cross_kv``; ``last_only``: LM head on the last position of every row only (greedy decoding)."""
     cfg = dec.config
     st = _store(dec)
     training = dec.training
@@ -608,10 +677,10 @@ def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: 
         h = ops.dropout(h, p_h, seed, _site(_RS_EMB, 0))
     encoder = dec.roberta.encoder
     L = len(encoder.layer)
-    enc_flat, Be, S, ebs, ers_ = _enc_layout(enc)
+    if kv is None:
+        kv = cross_kv(dec, enc)
+    enc_flat, Be, S, ebs, ers_, kv_all = kv.enc_flat, kv.B, kv.S, kv.bs, kv.rs, kv.kv_all   # kv_all: [S*B, L*2H]
     assert Be == B, "encoder_hidden_states batch mismatch"
-    xg = encoder._grp
-    kv_all = gemm(enc_flat, xg.w16, bias=xg.b)                                    # [S*B, L*2H] all cross K/V at once
     sv.enc_flat, sv.kv_all, sv.S, sv.enc_bs, sv.enc_rs = enc_flat, kv_all, S, ebs, ers_
     for li, (layer, cross, adp) in enumerate(encoder.layer):
         h, lsv = _dec_self_fwd(layer, h, B, T, nh, attention_mask, p_h, p_a, seed, li, save)
@@ -641,11 +710,14 @@ def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: 
         return h, None, None, sv
     # LM head (roberta.py:421-426); logits kept fp32, leading dimension padded to a multiple of 8
     lm = dec.lm_head
-    zh = torch.empty((B * T, Hd), dtype=BF16, device=dev) if save else None
+    if last_only:                                   # rows (b, T-1): a strided view, consumed in place by the GEMM
+        h = h.view(B, T, Hd)[:, T - 1]
+    rows = h.shape[0]
+    zh = torch.empty((rows, Hd), dtype=BF16, device=dev) if save else None
     g_ = gemm(h, lm.dense.weight._c16, bias=lm.dense.bias.data, act="gelu", aux_out=zh)
     xl, mul, rsl = _ln(g_, lm.layer_norm, save)
     Vp = (V + 7) // 8 * 8
-    logits_buf = torch.empty((B * T, Vp), dtype=F32, device=dev)
+    logits_buf = torch.empty((rows, Vp), dtype=F32, device=dev)
     logits = logits_buf[:, :V]
     gemm(xl, emb.word_embeddings.weight._c16, bias=lm.bias.data, out=logits)
     sv.head = SimpleNamespace(h=h, zh=zh, g=g_, mu=mul, rs=rsl, xl=xl, logits=logits) if save else None
@@ -774,10 +846,12 @@ def decoder_backward(dec, sv, gscale: Optional[torch.Tensor] = None, dlogits: Op
     if p_h > 0:
         dh = ops.dropout(dh, p_h, seed, _site(_RS_EMB, 0))
     de, _ = _ln_bwd(dh, sv.e, sv.emu, sv.ers, emb.LayerNorm)
-    ops.embed_bwd(de, sv.ids, sv.pos_ids, we._g32 if we.requires_grad else None,
-                  emb.position_embeddings.weight._g32 if emb.position_embeddings.weight.requires_grad else None,
-                  emb.token_type_embeddings.weight._g32 if emb.token_type_embeddings.weight.requires_grad else None,
-                  cfg.pad_token_id)
+    # the word-embedding gradient is shared with the tied LM-head wgrad (issued on the side stream): keep both on that stream
+    _off_critical_path(lambda: ops.embed_bwd(
+        de, sv.ids, sv.pos_ids, we._g32 if we.requires_grad else None,
+        emb.position_embeddings.weight._g32 if emb.position_embeddings.weight.requires_grad else None,
+        emb.token_type_embeddings.weight._g32 if emb.token_type_embeddings.weight.requires_grad else None,
+        cfg.pad_token_id), de)
     return denc
 
 
@@ -853,6 +927,7 @@ def _backward_train(model, esv, dsv, gscale):
     st.zero_grad()
     denc = decoder_backward(model.text_decoder, dsv, gscale=gscale)
     encoder_backward(model.expert_encoder, esv, denc)
+    _side_join(st.device)      # weight-gradient branch joins before the all-reduce / optimizer
 
 
 def _canon_experts(experts):

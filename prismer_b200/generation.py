@@ -24,10 +24,12 @@ def greedy(dec, input_ids, enc, attention_mask, max_length=20, min_length=0, ret
     unfinished = torch.ones(B, dtype=torch.int64, device=dev)
     cur = T0
     steps = []
+    kv = engine.cross_kv(dec, enc)              # visual K/V of all layers: once per call
+    ones = torch.ones((B, max_length), dtype=torch.int64, device=dev)
     while cur < max_length:
         cur_ids = ids[:, :cur].contiguous()
-        logits, _, _, _ = engine.decoder_forward(dec, cur_ids, torch.ones_like(cur_ids), enc, None, None, save=False)
-        last = logits.view(B, cur, -1)[:, -1]                       # strided rows of the fp32 logits buffer
+        last, _, _, _ = engine.decoder_forward(dec, cur_ids, ones[:, :cur].contiguous(), enc, None, None, save=False, kv=kv,
+                                               last_only=True)      # [B, V] fp32 logits of the last position
         tok = ops.argmax(last, V, suppress_eos=cur < min_length, eos=eos)
         if return_step_logits:
             steps.append(last.clone())

@@ -34,7 +34,7 @@ def _req_cuda(*ts):
 
 
 def _ld(t: torch.Tensor) -> int:
-    assert t.dim() == 2 and t.stride(1) == 1, f"need a 2-D row-major view, got {tuple(t.shape)} / {t.stride()}"
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), f"need a 2-D row-major view, got {tuple(t.shape)} / {t.stride()}"
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 

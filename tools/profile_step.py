@@ -46,3 +46,8 @@ S = sum(v[1] for v in tot.values())
 print(f"total kernel time {S/1e3:.2f} ms")
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])[:32]:
     print(f"{v[1]/1e3:8.3f} ms {100*v[1]/S:5.1f}%  n={v[0]:4d}  {k}")
+
+for kname in ("attn_fwd_kernel", "attn_bwd_dq_kernel", "attn_bwd_dkv_kernel", "ln_bwd_kernel"):
+    ds = [round((e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total), 1) for e in prof.events()
+          if e.device_type == torch.autograd.DeviceType.CUDA and kname in e.name]
+    print(kname, ds)
