@@ -188,15 +188,50 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the public API with HOST inputs: pinned H2D of the step's inputs + D2H of the loss every step
-    def e2e_step():
-        return step(ex_h, ids_h, mask_h, host_inputs=True).item()
+    # e2e: every step's inputs come from pinned host memory.  The H2D copy of batch i+1 runs on a copy stream into a staging
+    # set of device buffers while step i computes (ordinary input prefetching); a device-side copy moves it into the graph's
+    # static inputs at the start of step i+1.  Every step still pays one full H2D of its own inputs and a D2H of its loss.
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = {"ex": synthetic.experts_to(ex_h, dev), "ids": ids_h.to(dev), "mask": mask_h.to(dev), "labels": labels_h.to(dev)}
+    h2d_done, consumed = torch.cuda.Event(), torch.cuda.Event()
 
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed)
+            for k, v in ex_h.items():
+                if isinstance(v, dict):
+                    for kk, vv in v.items():
+                        staging["ex"][k][kk].copy_(vv, non_blocking=True)
+                else:
+                    staging["ex"][k].copy_(v, non_blocking=True)
+            staging["ids"].copy_(ids_h, non_blocking=True); staging["mask"].copy_(mask_h, non_blocking=True)
+            staging["labels"].copy_(labels_h, non_blocking=True)
+            h2d_done.record(copy_stream)
+
+    def e2e_step():
+        main = torch.cuda.current_stream()
+        main.wait_event(h2d_done)
+        if graphed is not None:
+            graphed.load_inputs(staging["ex"], staging["ids"], staging["mask"], staging["labels"])   # device -> static buffers
+            consumed.record(main)
+            prefetch()                                           # next batch's H2D overlaps this step's compute
+            return step(None, None, None).item()
+        ex = {k: ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone()) for k, v in staging["ex"].items()}
+        ids, mask = staging["ids"].clone(), staging["mask"].clone()
+        consumed.record(main)
+        prefetch()
+        return step(ex, ids, mask).item()
+
+    consumed.record(torch.cuda.current_stream())
+    prefetch()
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, max(2, args.steps // 2)) / max(2, args.steps // 2)
+    ms_e2e = timed(e2e_step, max(3, args.steps // 2)) / max(3, args.steps // 2)
+    torch.cuda.synchronize()
 
     # roofline pass: CUDA events around every GEMM launch of one (eager) step -- the dominant kernel family
     graphed_keep, graphed = graphed, None
+    engine.SIDE_STREAM = False          # isolated kernel durations: no concurrent gradient branch during the profiling passes
     step(ex_d, ids_d, mask_d)
     c1 = _C.CALLS
     ops.GEMM_PROFILE = []
@@ -212,6 +247,7 @@ def run_ours(args):
     for name, a, b in _C.PROFILE:
         t = fam.setdefault(name.replace("prismer_", ""), [0, 0.0]); t[0] += 1; t[1] += a.elapsed_time(b)
     _C.PROFILE = None
+    engine.SIDE_STREAM = True
     ops.GEMM_PROFILE = prof_gemm
     kernel_ms = {k: [v[0], round(v[1], 3)] for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])}
     graphed = graphed_keep
@@ -242,7 +278,8 @@ def run_ours(args):
         "config": {"workload": "Prismer-BASE caption fine-tune step (fwd+bwd+1 grad all-reduce+AdamW), 224x224 + 6 expert maps, "
                                "T=30, freeze_vision, dropout 0.1", "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": "per-step inputs (1.28 GB/GPU) exceed the 126 MB L2"},
-        "e2e": {"value": round(world * B / (ms_e2e / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "e2e": {"value": round(world * B / (ms_e2e / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": h2d + labels_h.numel() * 8,
+                "d2h_bytes_per_step": 4, "note": "pinned H2D of batch i+1 overlaps step i (copy stream); loss.item() every step"},
         "gpu_launches": launches, "cuda_graph": graphed is not None,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(achieved, 1), "peak": pk["bf16_tflops_sustained"],
@@ -270,8 +307,17 @@ def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):
     B = args.batch
     prefix = torch.tensor([[0, 250, 2170, 9]], device=dev).repeat(B, 1)
 
+    from prismer_b200 import generation
+    graphed = None if args.eager else generation.GraphedCaptioner(model, ex_d, prefix, max_length=20, min_length=8)
+
     def cap(ex):
         with torch.no_grad():
+            if graphed is not None:
+                if ex is not ex_d:
+                    graphed.load_inputs(ex)
+                return graphed()
+            if ex is not ex_d:
+                ex = synthetic.experts_to(ex, dev, non_blocking=True)
             enc = model.expert_encoder(ex).transpose(0, 1)
             return model.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=20, min_length=8)
 
@@ -288,11 +334,44 @@ def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # e2e: pinned-host inputs every batch (H2D of batch i+1 on a copy stream overlaps batch i), ids read back to the host
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = synthetic.experts_to(ex_h, dev)
+    h2d_done, consumed = torch.cuda.Event(), torch.cuda.Event()
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed)
+            for k, v in ex_h.items():
+                if isinstance(v, dict):
+                    for kk, vv in v.items():
+                        staging[k][kk].copy_(vv, non_blocking=True)
+                else:
+                    staging[k].copy_(v, non_blocking=True)
+            h2d_done.record(copy_stream)
+
+    def e2e_cap():
+        main = torch.cuda.current_stream()
+        main.wait_event(h2d_done)
+        if graphed is not None:
+            graphed.load_inputs(staging)
+            consumed.record(main)
+            prefetch()
+            return graphed().cpu()
+        ex = {k: ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone()) for k, v in staging.items()}
+        consumed.record(main)
+        prefetch()
+        return cap(ex).cpu()
+
+    consumed.record(torch.cuda.current_stream())
+    prefetch()
+    e2e_cap()
+    n2 = max(3, args.steps // 2)
     e0.record()
-    for _ in range(max(2, args.steps // 2)):
-        o = cap(synthetic.experts_to(ex_h, dev, non_blocking=True)).cpu()
+    for _ in range(n2):
+        o = e2e_cap()
     e1.record(); torch.cuda.synchronize()
-    ms2 = e0.elapsed_time(e1) / max(2, args.steps // 2)
+    ms2 = e0.elapsed_time(e1) / n2
     if rank == 0:
         print(json.dumps({"metric": "Prismer-BASE greedy captions/sec", "value": round(world * B / (float(t) / 1e3), 2), "unit": "captions/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(t), 3),
@@ -301,7 +380,8 @@ def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):
                                      "per_gpu_batch": B},
                           "e2e": {"value": round(world * B / (ms2 / 1e3), 2), "unit": "captions/s", "h2d_bytes_per_step": h2d,
                                   "d2h_bytes_per_step": int(o.numel() * 8)},
-                          "gpu_launches": (_C.CALLS - c0) // args.steps}), flush=True)
+                          "gpu_launches": (_C.CALLS - c0) // args.steps if graphed is None else "one cudaGraphLaunch (~3400 kernels)",
+                          "cuda_graph": graphed is not None}), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------- CPU arms

@@ -202,7 +202,7 @@ extern "C" int prismer_layernorm_bwd(const void* dy, long long lddy, const void*
   if (dz && drop_p > 0.f && !seed) return PRISMER_ERR_SHAPE;
   const int vpl = (D / 8 + 31) / 32;
   int grid = grid_for(rows);
-  if (dgamma && grid > 148 * 2) grid = 148 * 2;  // fewer, fatter blocks -> fewer atomics
+  if (dgamma && grid > 148 * 4) grid = 148 * 4;  // fewer, fatter blocks -> fewer atomics
   const int block = kWarpsPerBlock * 32;
   const size_t smem = dgamma ? sizeof(float) * kWarpsPerBlock * 2 * D : 0;
   const uint32_t thr16 = static_cast<uint32_t>(drop_p * 65536.0f + 0.5f);

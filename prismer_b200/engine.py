@@ -151,12 +151,14 @@ class ParamStore:
                 continue
             cout, cin, k, _ = p.shape
             K = cin * k * k
+            # the packed copies live in persistent buffers and are refreshed IN PLACE: captured CUDA graphs keep reading them
+            prev = getattr(p, "_pack16", None)
             if k == 3:
-                p._pack16 = ops.conv_weight_pack(p.data, (K + 7) // 8 * 8)
+                p._pack16 = ops.conv_weight_pack(p.data, (K + 7) // 8 * 8, out=prev)
             elif K % 8 == 0:
                 p._pack16 = p._c16.view(cout, K)   # 1x1 / patch conv: natural flatten == (c, kh, kw) K order
             else:
-                p._pack16 = ops.cast_pad(p.data.view(cout, K), (K + 7) // 8 * 8)
+                p._pack16 = ops.cast_pad(p.data.view(cout, K), (K + 7) // 8 * 8, out=prev)
 
     def zero_grad(self):
         self.grad_t.zero_()

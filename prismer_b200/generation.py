@@ -12,35 +12,111 @@ import torch
 from . import engine, ops
 
 
-@torch.no_grad()
-def greedy(dec, input_ids, enc, attention_mask, max_length=20, min_length=0, return_step_logits=False):
+def _greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None):
+    """Device-side greedy loop on a preallocated ``ids`` [B, max_length] buffer (prefix already in columns [0, T0)).
+    With ``early_exit=False`` there is no host synchronisation at all (finished rows keep emitting pad), so the whole loop
+    can be captured in a CUDA graph."""
     cfg = dec.config
     eos, pad, V = cfg.eos_token_id, cfg.pad_token_id, cfg.vocab_size
-    engine._store(dec).refresh()
-    B, T0 = input_ids.shape
-    dev = input_ids.device
-    ids = torch.full((B, max_length), pad, dtype=torch.int64, device=dev)
-    ids[:, :T0] = input_ids
+    B = ids.shape[0]
+    dev = ids.device
     unfinished = torch.ones(B, dtype=torch.int64, device=dev)
-    cur = T0
-    steps = []
-    kv = engine.cross_kv(dec, enc)              # visual K/V of all layers: once per call
+    kv = engine.cross_kv(dec, enc)              # visual K/V of all layers: once per call, not once per step and layer
     ones = torch.ones((B, max_length), dtype=torch.int64, device=dev)
+    cur = T0
     while cur < max_length:
         cur_ids = ids[:, :cur].contiguous()
         last, _, _, _ = engine.decoder_forward(dec, cur_ids, ones[:, :cur].contiguous(), enc, None, None, save=False, kv=kv,
                                                last_only=True)      # [B, V] fp32 logits of the last position
         tok = ops.argmax(last, V, suppress_eos=cur < min_length, eos=eos)
-        if return_step_logits:
+        if steps is not None:
             steps.append(last.clone())
         tok = tok * unfinished + pad * (1 - unfinished)
         ids[:, cur] = tok
         unfinished = unfinished * (tok != eos).long()
         cur += 1
-        if int(unfinished.max()) == 0:
+        if early_exit and int(unfinished.max()) == 0:
             break
+    return cur
+
+
+@torch.no_grad()
+def greedy(dec, input_ids, enc, attention_mask, max_length=20, min_length=0, return_step_logits=False):
+    engine._store(dec).refresh()
+    B, T0 = input_ids.shape
+    ids = torch.full((B, max_length), dec.config.pad_token_id, dtype=torch.int64, device=input_ids.device)
+    ids[:, :T0] = input_ids
+    steps = [] if return_step_logits else None
+    cur = _greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit=True, steps=steps)
     out = ids[:, :cur]
     return (out, steps) if return_step_logits else out
+
+
+def trim_finished(ids: torch.Tensor, T0: int, eos: int) -> torch.Tensor:
+    """HF stops as soon as every row has produced eos: cut the fixed-length output of the graphed loop at that column."""
+    gen = ids[:, T0:]
+    hit = (gen == eos)
+    if bool(hit.any(dim=1).all()):
+        last = int(hit.float().argmax(dim=1).max()) + 1
+        return ids[:, :T0 + last]
+    return ids
+
+
+class GraphedCaptioner:
+    """Encoder forward + the complete greedy decode (prismer_caption.py:36-50 with num_beams=1) captured in ONE CUDA graph
+    for a fixed (batch, prefix length, max_length): ~3400 kernel launches per batch become one ``cudaGraphLaunch``.
+    The instance-embedding table (host ``random.randint``, vit.py:144-146) is drawn before every replay."""
+
+    def __init__(self, model, experts, prefix_ids, max_length=20, min_length=8):
+        self.model = model
+        vit, dec = model.expert_encoder, model.text_decoder
+        st = self.store = engine._store(model)
+        st.refresh()
+        dev = st.device
+        self.experts = {k: ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone())
+                        for k, v in engine._canon_experts(experts).items()}
+        self.T0, self.max_length, self.min_length = prefix_ids.shape[1], max_length, min_length
+        self.prefix = prefix_ids.clone()
+        self.ids = torch.full((prefix_ids.shape[0], max_length), dec.config.pad_token_id, dtype=torch.int64, device=dev)
+        self.has_inst = "obj_detection" in self.experts
+        self.table = torch.zeros(256, dtype=torch.int32, device=dev) if self.has_inst else None
+
+        def run():
+            self.ids.fill_(dec.config.pad_token_id)
+            self.ids[:, :self.T0] = self.prefix
+            out, S, B, _ = engine.encoder_forward(vit, self.experts, save=False, inst_table=self.table)
+            enc = out.view(S, B, -1).transpose(0, 1)
+            _greedy_loop(dec, self.ids, self.T0, enc, max_length, min_length, early_exit=False)
+
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s), torch.no_grad():
+            self._draw_table()
+            run()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            run()
+
+    def _draw_table(self):
+        if self.has_inst:
+            self.table.copy_(engine._instance_table(self.experts["obj_detection"]["instance"]), non_blocking=True)
+
+    def load_inputs(self, experts, non_blocking=True):
+        for k, v in experts.items():
+            if isinstance(v, dict):
+                for kk, vv in v.items():
+                    self.experts[k][kk].copy_(vv, non_blocking=non_blocking)
+            else:
+                self.experts[k].copy_(v, non_blocking=non_blocking)
+
+    def __call__(self) -> torch.Tensor:
+        """Replay on the current static inputs; returns the [B, max_length] id buffer (use ``trim_finished`` for HF's length)."""
+        self.store.refresh()
+        self._draw_table()
+        self.graph.replay()
+        return self.ids
 
 
 @torch.no_grad()

@@ -362,9 +362,10 @@ def bn_relu_bwd(dAcol, y2d, scale, shift, mean, rstd, gamma, dgamma, dbeta, B, H
     return dy
 
 
-def conv_weight_pack(w, Kpad):
+def conv_weight_pack(w, Kpad, out=None):
     Cout, Cin, k, _ = w.shape
-    out = torch.empty((Cout, Kpad), dtype=BF16, device=w.device)
+    if out is None or out.shape != (Cout, Kpad):
+        out = torch.empty((Cout, Kpad), dtype=BF16, device=w.device)
     check(_C.lib().prismer_conv_weight_pack(w.data_ptr(), out.data_ptr(), Cout, Cin, k, Kpad, _stream()), "conv_weight_pack")
     return out
 
@@ -374,9 +375,10 @@ def conv_weight_unpack_grad(dwp, grad):
     check(_C.lib().prismer_conv_weight_unpack_grad(dwp.data_ptr(), grad.data_ptr(), Cout, Cin, k, dwp.shape[1], _stream()), "conv_unpack")
 
 
-def cast_pad(src2d, Cpad):
+def cast_pad(src2d, Cpad, out=None):
     R, C = src2d.shape
-    out = torch.empty((R, Cpad), dtype=BF16, device=src2d.device)
+    if out is None or out.shape != (R, Cpad):
+        out = torch.empty((R, Cpad), dtype=BF16, device=src2d.device)
     check(_C.lib().prismer_cast_pad(src2d.data_ptr(), out.data_ptr(), R, C, Cpad, _stream()), "cast_pad")
     return out
 
