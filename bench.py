@@ -388,7 +388,9 @@ def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):
 def cpu_train_baseline(model, sample_batch=2, iters=2, threads=None):
     """The reference's CPU PyTorch path (oracle port: same modules' math, fp32, eager) on a bounded sample of the workload."""
     from oracle import prismer_oracle as O
-    threads = threads or os.cpu_count()
+    # all the host threads eager PyTorch can use productively: beyond ~32 threads the small per-op work of this path is
+    # oversubscribed (measured on the 128-core GPU host: 128 threads -> 12.2 s/step, 8 threads -> 1.4 s/step for batch 2)
+    threads = threads or min(os.cpu_count() or 1, 32)
     torch.set_num_threads(threads)
     sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
     ex, ids, mask = build_inputs(sample_batch, 7)
