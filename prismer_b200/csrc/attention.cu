@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 template <int D>
-__global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(AttnParams p) {
+__global__ void __launch_bounds__(NWARP * 32, (D <= 64) ? 3 : 1) attn_bwd_dkv_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int TILE = 64 * (D + PAD);
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);

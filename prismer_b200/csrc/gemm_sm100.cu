@@ -206,12 +206,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rows_valid = min(32, M - (m0 + q * 32));   // rows of this warp's 32-row slab that exist (may be <= 0)
 #pragma unroll 1
       for (int c = chalf * 32; c < BN; c += 64) {
+        const int col0 = n0 + c;
+        const bool full = (col0 + 32 <= N);                  // warp-uniform
+        // the bf16 side input of this chunk (saved pre-activation for act_grad, else the residual) is requested BEFORE the TMEM
+        // load is waited for, so its global latency overlaps the accumulator read
+        const bf16* side = ep.act_grad ? ep.aux_in : ep.residual;
+        const bool side_pre = side != nullptr && full && row_ok;
+        uint4 pre[4];
+        if (side_pre) {
+          const uint4* sp = reinterpret_cast<const uint4*>(side + static_cast<long long>(row) * (ep.act_grad ? ep.ldaux : ep.ldr) + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pre[j] = sp[j];
+        }
         uint32_t raw[32];
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c, raw);
         ptx::tmem_ld_wait();
-        const int col0 = n0 + c;
         if (col0 >= N || rows_valid <= 0) continue;          // warp-uniform
-        const bool full = (col0 + 32 <= N);                  // warp-uniform
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * ep.alpha;
@@ -241,9 +251,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bf16* ap = ep.aux_in + static_cast<long long>(row) * ep.ldaux + col0;
             if (full) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float z[8]; unpack8(*reinterpret_cast<const bf16x8*>(ap + j), z);
-                act_bwd8(ep.act_grad, v + j, z);
+              for (int j = 0; j < 4; ++j) {
+                float z[8]; unpack8(pre[j], z);
+                act_bwd8(ep.act_grad, v + 8 * j, z);
               }
             } else {
               _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { v[j] *= act_bwd(ep.act_grad, __bfloat162float(ap[j])); }
@@ -264,7 +274,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // ---- residual
           if (ep.residual) {
             const bf16* rp = ep.residual + static_cast<long long>(row) * ep.ldr + col0;
-            if (full) {
+            if (full && !ep.act_grad) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float r[8]; unpack8(pre[j], r);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[8 * j + t] += r[t];
+              }
+            } else if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 float r[8]; unpack8(*reinterpret_cast<const bf16x8*>(rp + j), r);
