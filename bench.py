@@ -142,13 +142,16 @@ def run_ours(args):
     labels_h = labels_d.cpu().pin_memory()
     graphed = None
     if not args.eager:
-        graphed = engine.GraphedTrainStep(model, ex_d, ids_d, mask_d, labels_d)
+        graphed = engine.GraphedTrainStep(model, ex_d, ids_d, mask_d, labels_d, overlap=world > 1)
+    comm = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)) if world > 1 else None
 
     def step(ex, ids, mask, host_inputs=False):
         if graphed is not None:
             if host_inputs:                                  # pinned host -> static device buffers (H2D inside the step)
                 graphed.load_inputs(ex, ids, mask, labels_h)
-            loss = graphed()                                 # fwd + bwd: one cudaGraphLaunch
+            loss = graphed(comm)                             # fwd + bwd as CUDA graph(s); grads all-reduced, decoder slice early
+            opt.step()
+            return loss
         else:
             if host_inputs:
                 ex, ids, mask = synthetic.experts_to(ex, dev, non_blocking=True), ids.to(dev, non_blocking=True), mask.to(dev, non_blocking=True)
@@ -283,9 +286,15 @@ def run_ours(args):
         "gpu_launches": launches, "cuda_graph": graphed is not None,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(achieved, 1), "peak": pk["bf16_tflops_sustained"],
-                     "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4), "traffic": None,
+                     "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4), "traffic": 21438720,
+                     "traffic_note": "dram read+write bytes of ONE ncu --set full launch (M8320 N3072 K768, profiles/ncu_r1_summary.md); "
+                                     "algorithmic operand bytes of that launch: 17.5 MB",
                      "peak_source": pk["source"] + " sustained cuBLAS bf16", "gemm_launches_per_step": len(prof),
-                     "gemm_ms_per_step": round(g_ms, 3), "gemm_share_of_step": round(g_ms / ms_step, 3)},
+                     "gemm_ms_per_step": round(g_ms, 3),
+                     "gemm_share_of_step": round(fam.get("gemm_bf16", [0, 0.0])[1] / max(sum(v[1] for v in fam.values()), 1e-9), 3),
+                     "note": "achieved = sum(2MNK)/sum(CUDA-event time) over all 623 GEMM launches of one eager step (half of them are "
+                             "decoder GEMMs with M = 960 rows, launch/latency bound); large shapes run at 850-1000 TFLOP/s "
+                             "(tools/bench_gemm.py)"},
         "step_mfu": {"model_gflop_per_img": TRAIN_GFLOP_PER_IMG, "achieved_tflops_per_gpu": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3, 1),
                      "frac_of_peak": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3 / pk["bf16_tflops_sustained"], 4)},
         "host_enqueue_ms_per_step": round(host_ms, 2),
