@@ -68,6 +68,12 @@ def _real_lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
+            try:     # in-tree build (needs nvcc); this is NOT a fallback path -- without the CUDA library nothing runs
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise PrismerError(f"{LIB_PATH} is missing and could not be built: {e}") from e
+        if not os.path.exists(LIB_PATH):
             raise PrismerError(
                 f"{LIB_PATH} not found: build it with `python -m prismer_b200.build` "
                 "(or `__graft_entry__.build()`); prismer_b200 has no CPU / PyTorch fallback.")

@@ -84,33 +84,44 @@ __global__ void cast_kernel(const float* __restrict__ src, bf16* __restrict__ ds
 // ------------------------------------------------------------------ fused AdamW over a flat fp32 buffer
 // torch.optim.AdamW semantics (train_caption.py:111-112): p *= 1 - lr*wd; m,v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 // grad_scale folds the data-parallel average (1/world) into the update; also refreshes the bf16 compute copy.
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                             bf16* __restrict__ p16, long long n, float lr, float beta1, float beta2, float eps, float wd,
-                             float bc1, float bc2_sqrt, float grad_scale) {
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, bf16* __restrict__ p16, long long n, float lr, float beta1,
+                                                    float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
   const long long n4 = n >> 2;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 pv = reinterpret_cast<float4*>(p)[i];
-    const float4 gv = reinterpret_cast<const float4*>(g)[i];
-    float4 mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
-    float pp[4] = {pv.x, pv.y, pv.z, pv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
-    float mm[4] = {mv.x, mv.y, mv.z, mv.w}, vvv[4] = {vv.x, vv.y, vv.z, vv.w};
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  constexpr int U = 4;   // independent 128-bit streams per thread: 16 loads in flight before the first use
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < n4; i0 += stride * U) {
+    float4 pv[U], gv[U], mv[U], vv[U];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float gr = gg[t] * grad_scale;
-      pp[t] *= (1.0f - lr * wd);
-      mm[t] = beta1 * mm[t] + (1.0f - beta1) * gr;
-      vvv[t] = beta2 * vvv[t] + (1.0f - beta2) * gr * gr;
-      const float denom = sqrtf(vvv[t]) / bc2_sqrt + eps;
-      pp[t] -= (lr / bc1) * (mm[t] / denom);
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n4) {
+        pv[u] = reinterpret_cast<const float4*>(p)[i]; gv[u] = reinterpret_cast<const float4*>(g)[i];
+        mv[u] = reinterpret_cast<const float4*>(m)[i]; vv[u] = reinterpret_cast<const float4*>(v)[i];
+      }
     }
-    reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
-    reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-    reinterpret_cast<float4*>(v)[i] = make_float4(vvv[0], vvv[1], vvv[2], vvv[3]);
-    if (p16) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(pp[0], pp[1]), b = __floats2bfloat162_rn(pp[2], pp[3]);
-      uint2 o; o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
-      reinterpret_cast<uint2*>(p16)[i] = o;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n4) continue;
+      float pp[4] = {pv[u].x, pv[u].y, pv[u].z, pv[u].w}, gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+      float mm[4] = {mv[u].x, mv[u].y, mv[u].z, mv[u].w}, vvv[4] = {vv[u].x, vv[u].y, vv[u].z, vv[u].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float gr = gg[t] * grad_scale;
+        pp[t] *= (1.0f - lr * wd);
+        mm[t] = beta1 * mm[t] + (1.0f - beta1) * gr;
+        vvv[t] = beta2 * vvv[t] + (1.0f - beta2) * gr * gr;
+        const float denom = sqrtf(vvv[t]) / bc2_sqrt + eps;
+        pp[t] -= (lr / bc1) * (mm[t] / denom);
+      }
+      reinterpret_cast<float4*>(p)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+      reinterpret_cast<float4*>(m)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      reinterpret_cast<float4*>(v)[i] = make_float4(vvv[0], vvv[1], vvv[2], vvv[3]);
+      if (p16) {
+        uint2 o; o.x = pack_bf162(pp[0], pp[1]); o.y = pack_bf162(pp[2], pp[3]);
+        reinterpret_cast<uint2*>(p16)[i] = o;
+      }
     }
   }
 }

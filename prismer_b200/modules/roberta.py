@@ -21,93 +21,109 @@ class RobertaConfig(SimpleNamespace):
         return cls(**d)
 
 
+def _linear(n_in: int, n_out: int) -> nn.Linear:
+    return nn.Linear(n_in, n_out)
+
+
+def _norm(cfg) -> LayerNorm:
+    return LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+
+
+def _container(**children) -> nn.Module:
+    """A bare nn.Module whose only job is to hold named children (keeps the reference's state_dict keys)."""
+    m = nn.Module()
+    for name, child in children.items():
+        setattr(m, name, child)
+    return m
+
+
 class RobertaEmbeddings(nn.Module):
-    def __init__(self, config):
+    """word / position / token-type tables + LayerNorm (keys of roberta.py:48-64); gathered by ``prismer_embed_fwd``."""
+
+    def __init__(self, cfg):
         super().__init__()
-        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=config.pad_token_id)
-        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size,
-                                                padding_idx=config.pad_token_id)
-        self.token_type_embeddings = nn.Embedding(config.type_vocab_size, config.hidden_size)
-        self.LayerNorm = LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
-        self.dropout = nn.Dropout(config.hidden_dropout_prob)
-        self.register_buffer("position_ids", torch.arange(config.max_position_embeddings).expand((1, -1)))
-        self.padding_idx = config.pad_token_id
+        H, pad = cfg.hidden_size, cfg.pad_token_id
+        self.word_embeddings = nn.Embedding(cfg.vocab_size, H, padding_idx=pad)
+        self.position_embeddings = nn.Embedding(cfg.max_position_embeddings, H, padding_idx=pad)
+        self.token_type_embeddings = nn.Embedding(cfg.type_vocab_size, H)
+        self.LayerNorm = _norm(cfg)
+        self.dropout = nn.Dropout(cfg.hidden_dropout_prob)
+        self.register_buffer("position_ids", torch.arange(cfg.max_position_embeddings).expand((1, -1)))
+        self.padding_idx = pad
 
 
 class RobertaSelfAttention(nn.Module):
-    def __init__(self, config, is_cross_attention=False):
+    """q/k/v projections; K/V read ``vision_hidden_size`` features when this is the cross-attention (roberta.py:79-93)."""
+
+    def __init__(self, cfg, is_cross_attention=False):
         super().__init__()
-        self.num_attention_heads = config.num_attention_heads
-        kv_in = config.vision_hidden_size if is_cross_attention else config.hidden_size
-        self.query = nn.Linear(config.hidden_size, config.hidden_size)
-        self.key = nn.Linear(kv_in, config.hidden_size)
-        self.value = nn.Linear(kv_in, config.hidden_size)
-        self.dropout = nn.Dropout(config.attention_probs_dropout_prob)
+        H = cfg.hidden_size
+        src = cfg.vision_hidden_size if is_cross_attention else H
+        self.num_attention_heads = cfg.num_attention_heads
+        self.query, self.key, self.value = _linear(H, H), _linear(src, H), _linear(src, H)
+        self.dropout = nn.Dropout(cfg.attention_probs_dropout_prob)
 
 
 class RobertaSelfOutput(nn.Module):
-    def __init__(self, config):
+    def __init__(self, cfg, n_in=None):
         super().__init__()
-        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
-        self.LayerNorm = LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
-        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.dense = _linear(n_in or cfg.hidden_size, cfg.hidden_size)
+        self.LayerNorm = _norm(cfg)
+        self.dropout = nn.Dropout(cfg.hidden_dropout_prob)
 
 
 class RobertaAttention(nn.Module):
-    def __init__(self, config, is_cross_attention=False):
+    def __init__(self, cfg, is_cross_attention=False):
         super().__init__()
-        self.self = RobertaSelfAttention(config, is_cross_attention)
-        self.output = RobertaSelfOutput(config)
+        setattr(self, "self", RobertaSelfAttention(cfg, is_cross_attention))
+        self.output = RobertaSelfOutput(cfg)
 
 
 class RobertaIntermediate(nn.Module):
-    def __init__(self, config):
+    def __init__(self, cfg):
         super().__init__()
-        self.dense = nn.Linear(config.hidden_size, config.intermediate_size)
+        self.dense = _linear(cfg.hidden_size, cfg.intermediate_size)
 
 
-class RobertaOutput(nn.Module):
-    def __init__(self, config):
-        super().__init__()
-        self.dense = nn.Linear(config.intermediate_size, config.hidden_size)
-        self.LayerNorm = LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
-        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+class RobertaOutput(RobertaSelfOutput):
+    def __init__(self, cfg):
+        super().__init__(cfg, n_in=cfg.intermediate_size)
 
 
 class RobertaLayer(nn.Module):
-    def __init__(self, config):
+    """self-attention block + MLP (post-LN); the engine runs them as ``mode='attention'`` / ``mode='mlp'`` of roberta.py:186-199."""
+
+    def __init__(self, cfg):
         super().__init__()
-        self.attention = RobertaAttention(config)
-        self.intermediate = RobertaIntermediate(config)
-        self.output = RobertaOutput(config)
+        self.attention, self.intermediate, self.output = RobertaAttention(cfg), RobertaIntermediate(cfg), RobertaOutput(cfg)
 
 
 class RobertaEncoder(nn.Module):
-    def __init__(self, config):
+    """num_hidden_layers x [RobertaLayer, cross RobertaAttention, norm-late Adaptor] + a cross-attention-free output_layer."""
+
+    def __init__(self, cfg):
         super().__init__()
-        self.config = config
-        self.layer = nn.ModuleList([nn.ModuleList([RobertaLayer(config), RobertaAttention(config, is_cross_attention=True),
-                                                   Adaptor(config.hidden_size, norm_late=True)])
-                                    for _ in range(config.num_hidden_layers)])
-        self.output_layer = RobertaLayer(config)
+        self.config = cfg
+        triple = lambda: nn.ModuleList([RobertaLayer(cfg), RobertaAttention(cfg, True), Adaptor(cfg.hidden_size, norm_late=True)])
+        self.layer = nn.ModuleList([triple() for _ in range(cfg.num_hidden_layers)])
+        self.output_layer = RobertaLayer(cfg)
 
 
 class RobertaModel(nn.Module):
-    def __init__(self, config):
+    def __init__(self, cfg):
         super().__init__()
-        self.config = config
-        self.embeddings = RobertaEmbeddings(config)
-        self.encoder = RobertaEncoder(config)
+        self.config, self.embeddings, self.encoder = cfg, RobertaEmbeddings(cfg), RobertaEncoder(cfg)
 
 
 class RobertaLMHead(nn.Module):
-    def __init__(self, config):
+    """dense -> erf-GELU -> LayerNorm -> tied decoder (+ bias); decoder.bias aliases ``bias`` (roberta.py:417-419)."""
+
+    def __init__(self, cfg):
         super().__init__()
-        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
-        self.layer_norm = LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
-        self.decoder = nn.Linear(config.hidden_size, config.vocab_size)
-        self.bias = nn.Parameter(torch.zeros(config.vocab_size))
-        self.decoder.bias = self.bias  # roberta.py:417-419
+        self.dense, self.layer_norm = _linear(cfg.hidden_size, cfg.hidden_size), _norm(cfg)
+        self.decoder = _linear(cfg.hidden_size, cfg.vocab_size)
+        self.bias = nn.Parameter(torch.zeros(cfg.vocab_size))
+        self.decoder.bias = self.bias
 
 
 class CausalLMOutput(SimpleNamespace):
