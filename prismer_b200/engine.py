@@ -298,12 +298,13 @@ def _mlp_fwd(x, fc: nn.Linear, proj: nn.Linear, act: str, residual, save: bool, 
     return y, (z, a)
 
 
-def _mlp_bwd(dy, x, z, a, fc: nn.Linear, proj: nn.Linear, act: str):
-    """dy: gradient wrt (a.Wproj^T + b) [after any dropout mask was applied]; returns dx."""
+def _mlp_bwd(dy, x, z, a, fc: nn.Linear, proj: nn.Linear, act: str, residual=None):
+    """dy: gradient wrt (a.Wproj^T + b) [after any dropout mask was applied]; returns dx (+ ``residual``: the gradient that
+    by-passed the MLP through the skip connection is added in the last dgrad's epilogue instead of a separate add kernel)."""
     dz = gemm(dy, proj.weight._c16, trans_b=True, act_grad=act, aux_in=z)
     _lin_grads(dy, a, proj)
     _lin_grads(dz, x, fc)
-    return gemm(dz, fc.weight._c16, trans_b=True)
+    return gemm(dz, fc.weight._c16, trans_b=True, residual=residual)
 
 
 def _sf(t2d, L, B):
@@ -769,8 +770,7 @@ def _dec_mlp_fwd(layer, h, p_h, seed, li, save):
 def _dec_mlp_bwd(layer, dh, sv, p_h, seed, li):
     dpre, dz_ = _ln_bwd(dh, sv.pre, sv.mu, sv.rs, layer.output.LayerNorm, dz=True, drop_p=p_h, seed=seed,
                         stream=_site(_RS_MLP_O, li))
-    dhin_branch = _mlp_bwd(dz_, sv.hin, sv.z, sv.a, layer.intermediate.dense, layer.output.dense, "gelu")
-    return dpre, dhin_branch     # caller adds: d(hin) = dpre (residual) + branch
+    return _mlp_bwd(dz_, sv.hin, sv.z, sv.a, layer.intermediate.dense, layer.output.dense, "gelu", residual=dpre)   # d(hin)
 
 
 def _add(a, b):
@@ -821,20 +821,17 @@ def decoder_backward(dec, sv, gscale: Optional[torch.Tensor] = None, dlogits: Op
     _lin_grads(dzh, hd.h, lm.dense)
     dh = gemm(dzh, lm.dense.weight._c16, trans_b=True)
     # output layer
-    dpre, dbr = _dec_mlp_bwd(encoder.output_layer, dh, sv.out_mlp, p_h, seed, L)
-    dh = _add(dbr, dpre)
+    dh = _dec_mlp_bwd(encoder.output_layer, dh, sv.out_mlp, p_h, seed, L)
     dh = _dec_self_bwd(encoder.output_layer, dh, sv.out_self, B, T, nh, sv.mask, p_h, p_a, seed, L)
     dkv_all = torch.empty_like(sv.kv_all)      # every layer's backward fills its own [dK | dV] column slice
     for li in reversed(range(L)):
         layer, cross, adp = encoder.layer[li]
         lsv = sv.layers[li]
         c = lsv.cross
-        dpre, dbr = _dec_mlp_bwd(layer, dh, lsv.mlp, p_h, seed, li)
-        dh_a = _add(dbr, dpre)
+        dh_a = _dec_mlp_bwd(layer, dh, lsv.mlp, p_h, seed, li)
         # adaptor (norm late): h_a = LN(up(sqrelu(down(h_c))) + h_c)
         dprea, _ = _ln_bwd(dh_a, c.prea, c.mua, c.rsa, adp.adaptor_ln)
-        dbr = _mlp_bwd(dprea, c.h_c, c.za, c.a, adp.adaptor.down_proj, adp.adaptor.up_proj, "sqrelu")
-        dh_c = _add(dbr, dprea)
+        dh_c = _mlp_bwd(dprea, c.h_c, c.za, c.a, adp.adaptor.down_proj, adp.adaptor.up_proj, "sqrelu", residual=dprea)
         # cross attention
         dpre, dz_ = _ln_bwd(dh_c, c.pre, c.mu, c.rs, cross.output.LayerNorm, dz=True, drop_p=p_h, seed=seed,
                             stream=_site(_RS_CROSS_O, li))
