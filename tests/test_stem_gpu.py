@@ -85,4 +85,6 @@ def test_stem_fwd_bwd(domain, B, size, patch):
     # (measured rate 1e-4..1e-3, printed above) and each flip injects an O(1) element error into noise-like gradients:
     # rel-L2 ~ sqrt(2 * flip_rate) = 2-5%.  The kernels themselves are exact to 2e-3 (tests/test_bn_kernels_gpu.py).
     assert ferr < 1.5e-2
-    assert max(errs.values()) < 9e-2, errs
+    # with very few samples per channel in the last BatchNorm (B*gh*gw < 200) a single flip moves the statistics themselves,
+    # so the bound is wider there; the large cases bound the systematic error
+    assert max(errs.values()) < (0.15 if B * gh * gw < 200 else 9e-2), errs
