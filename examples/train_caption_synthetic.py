@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""The reference's caption fine-tune loop (train_caption.py:111-136) running on prismer_b200 -- same loop body, same config
+keys, string captions in, synthetic data instead of COCO (no datasets here).
+
+    python examples/train_caption_synthetic.py --steps 20                       # 1 GPU
+    torchrun --nproc-per-node 8 examples/train_caption_synthetic.py             # data parallel, one all-reduce per step
+"""
+import argparse
+import math
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from prismer_b200 import synthetic                                   # noqa: E402
+from prismer_b200.accelerate_shim import Accelerator                 # reference: from accelerate import Accelerator
+from prismer_b200.optim import FusedAdamW                            # reference: torch.optim.AdamW (also works)
+from prismer_b200.prismer_caption import PrismerCaption              # reference: from model.prismer_caption import PrismerCaption
+
+
+def cosine_lr_schedule(optimizer, epoch, max_epoch, init_lr, min_lr):
+    """utils.py:13-17 of the reference."""
+    lr = (init_lr - min_lr) * 0.5 * (1. + math.cos(math.pi * epoch / max_epoch)) + min_lr
+    for param_group in optimizer.param_groups:
+        param_group['lr'] = lr
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--batch', type=int, default=8)
+    ap.add_argument('--seed', type=int, default=42)
+    ap.add_argument('--torch_adamw', action='store_true')
+    args = ap.parse_args()
+    config = {'experts': synthetic.DEFAULT_EXPERTS, 'image_resolution': 224, 'prismer_model': 'prismer_base', 'freeze': 'freeze_vision',
+              'batch_size_train': args.batch, 'init_lr': 5e-5, 'weight_decay': 0.05, 'min_lr': 0, 'max_epoch': 1,
+              'prefix': 'A picture of'}                                         # configs/caption.yaml
+    torch.manual_seed(args.seed); np.random.seed(args.seed); random.seed(args.seed)
+
+    accelerator = Accelerator(mixed_precision='bf16')
+    model = PrismerCaption(config)
+    if args.torch_adamw:
+        model.to(accelerator.device)
+        optimizer = torch.optim.AdamW(params=filter(lambda p: p.requires_grad, model.parameters()), lr=config['init_lr'],
+                                      weight_decay=config['weight_decay'])
+        model = accelerator.prepare(model)
+    else:
+        model = accelerator.prepare(model)
+        optimizer = accelerator.prepare(FusedAdamW(model, lr=config['init_lr'], weight_decay=config['weight_decay']))
+
+    words = "a an the dog cat man woman street table plate bus train sitting standing holding red blue green two three".split()
+    rng = random.Random(args.seed + accelerator.process_index)
+    experts = synthetic.experts_to(synthetic.synth_experts(args.batch, 224, config['experts'], 224, accelerator.process_index), accelerator.device)
+    model.train()
+    for i in range(args.steps):
+        caption = [config['prefix'] + ' ' + ' '.join(rng.choice(words) for _ in range(rng.randint(4, 10))) for _ in range(args.batch)]
+        cosine_lr_schedule(optimizer, i, args.steps, config['init_lr'], config['min_lr'])
+
+        loss = model(experts, caption, prefix=config['prefix'])
+
+        optimizer.zero_grad()
+        accelerator.backward(loss)
+        if args.torch_adamw and accelerator.num_processes > 1:
+            for p in model.parameters():
+                if p.grad is not None:
+                    p.grad.div_(accelerator.num_processes)
+        optimizer.step()
+        accelerator.print(f"step {i:3d}  loss {loss.item():.4f}  lr {optimizer.param_groups[0]['lr']:.2e}")
+
+    model.eval()
+    with torch.no_grad():
+        captions = model(experts, train=False, prefix=config['prefix'])
+    accelerator.print("generated:", captions[:2])
+
+
+if __name__ == '__main__':
+    main()

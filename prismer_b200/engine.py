@@ -25,8 +25,6 @@ import torch.nn as nn
 from . import ops
 from .ops import BF16, F32, gemm
 
-LN_EPS = 1e-5
-
 # dropout call-site ids (Philox streams)
 _RS_EMB, _RS_SELF_P, _RS_SELF_O, _RS_CROSS_P, _RS_CROSS_O, _RS_MLP_O = 1, 2, 3, 4, 5, 6
 
@@ -771,12 +769,6 @@ def _dec_mlp_bwd(layer, dh, sv, p_h, seed, li):
     dpre, dz_ = _ln_bwd(dh, sv.pre, sv.mu, sv.rs, layer.output.LayerNorm, dz=True, drop_p=p_h, seed=seed,
                         stream=_site(_RS_MLP_O, li))
     return _mlp_bwd(dz_, sv.hin, sv.z, sv.a, layer.intermediate.dense, layer.output.dense, "gelu", residual=dpre)   # d(hin)
-
-
-def _add(a, b):
-    """a += b on bf16 [M, H] rows (gradient joins)."""
-    ops.copy_rows(b, a, add=True)
-    return a
 
 
 def _dec_self_bwd(layer, dh, sv, B, T, nh, mask, p_h, p_a, seed, li):
