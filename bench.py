@@ -237,13 +237,23 @@ def run_ours(args):
     engine.SIDE_STREAM = False          # isolated kernel durations: no concurrent gradient branch during the profiling passes
     step(ex_d, ids_d, mask_d)
     c1 = _C.CALLS
+    def queue_ahead():
+        """Keep the GPU busy for ~80 ms so that the whole eager step is enqueued behind it: the CUDA events around each launch
+        then bracket back-to-back device execution instead of host launch latency (the step itself runs as a CUDA graph)."""
+        try:
+            torch.cuda._sleep(int(0.08 * 1.9e9))
+        except Exception:
+            pass
+
     ops.GEMM_PROFILE = []
+    queue_ahead()
     step(ex_d, ids_d, mask_d)
     torch.cuda.synchronize()
     launches = _C.CALLS - c1
     # per-entry-point device time of one eager step (CUDA events around every C-ABI call)
     prof_gemm, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
     _C.PROFILE = []
+    queue_ahead()
     step(ex_d, ids_d, mask_d)
     torch.cuda.synchronize()
     fam = {}
