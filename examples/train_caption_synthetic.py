@@ -63,10 +63,6 @@ def main():
 
         optimizer.zero_grad()
         accelerator.backward(loss)
-        if args.torch_adamw and accelerator.num_processes > 1:
-            for p in model.parameters():
-                if p.grad is not None:
-                    p.grad.div_(accelerator.num_processes)
         optimizer.step()
         accelerator.print(f"step {i:3d}  loss {loss.item():.4f}  lr {optimizer.param_groups[0]['lr']:.2e}")
 

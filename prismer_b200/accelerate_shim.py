@@ -28,6 +28,7 @@ class Accelerator:
         else:
             self.device = torch.device("cpu")
         self._models = []
+        self._fused_optimizer = False
 
     @property
     def is_main_process(self):
@@ -50,6 +51,7 @@ class Accelerator:
                 self._models.append(o)
             elif hasattr(o, "grad_scale"):
                 o.grad_scale = 1.0 / self.num_processes
+                self._fused_optimizer = True
             out.append(o)
         return out[0] if len(out) == 1 else tuple(out)
 
@@ -57,7 +59,8 @@ class Accelerator:
         loss.backward()
         if self.use_distributed:
             for m in self._models:
-                allreduce_gradients(m)
+                # with the fused optimizer the 1/world average is folded into its kernel; a stock torch optimizer needs it here
+                allreduce_gradients(m, average=not self._fused_optimizer)
 
     def wait_for_everyone(self):
         if self.use_distributed:
@@ -81,10 +84,12 @@ class Accelerator:
                 torch.save(m.state_dict(), os.path.join(output_dir, "pytorch_model.bin"))
 
 
-def allreduce_gradients(model, group=None):
+def allreduce_gradients(model, group=None, average: bool = False):
     """The one collective of the step: all-reduce(sum) of the flat fp32 gradient buffer (242 M elements for BASE
     freeze_vision).  The average's 1/world is applied inside the fused AdamW kernel (``FusedAdamW.grad_scale``); when a stock
     torch optimizer is used instead, pass ``average=True`` to divide here."""
     st = engine._store(model)
     dist.all_reduce(st.grad_t, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        st.grad_t.div_(dist.get_world_size(group))
     return st.grad_t
