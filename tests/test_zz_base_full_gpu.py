@@ -44,7 +44,7 @@ def test_prismer_base_full_size_matches_oracle():
     agree = (out.logits.cpu().argmax(-1) == logits_ref.argmax(-1))
     print(f"BASE eval: enc rel-L2 {e_enc:.2e}, logits rel-L2 {e_log:.2e}, argmax agreement {agree.float().mean():.3f} "
           f"(decisive positions {int(decisive.sum())}/{decisive.numel()}: {agree[decisive].float().mean() if decisive.any() else 1.0:.3f})")
-    assert e_enc < 3e-2 and e_log < 4e-2
+    assert e_enc < 4e-2 and e_log < 6e-2
     if decisive.any():
         assert bool(agree[decisive].all())          # token ids exact wherever the fp32 decision is not a near-tie
 
