@@ -196,6 +196,32 @@ int prismer_conv_weight_unpack_grad(const float* dwp, float* grad, int Cout, int
 int prismer_cast_pad(const float* src, void* dst, long long R, int C, int Cpad, cudaStream_t stream);
 int prismer_unpad_add(const float* src, float* dst, long long R, int C, int Cpad, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * EXPERIMENTAL (round-2 candidate; compiled and exported but not on the default path and not yet validated on hardware):
+ * attention as batched tcgen05 GEMMs over (batch, head) problems with L2-resident score matrices.
+ *   C_i[M,N] = epilogue(alpha * op(A_i) . op(B_i)^T),  X_i = X + bo * X_bs_outer + bi * X_bs_inner (elements)
+ *   mode 0: C = alpha*acc;   mode 1 (softmax backward): C = aux * (acc - rowvec[i*rowvec_bs + row]) * alpha
+ * Replaces (when enabled) the score / value products of nn.MultiheadAttention (vit.py:52-53) and their backward.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct PrismerBatchedGemmArgs {
+  const void* A; const void* B; void* C;
+  int M, N, K;
+  long long lda, ldb, ldc;
+  int transA, transB;
+  int batch_outer, batch_inner;
+  long long a_bs_outer, a_bs_inner, b_bs_outer, b_bs_inner, c_bs_outer, c_bs_inner;
+  const void* aux; long long ldaux, aux_bs_outer, aux_bs_inner;
+  const float* rowvec; long long rowvec_bs;
+  int mode;
+  float alpha;
+} PrismerBatchedGemmArgs;
+int prismer_gemm_bf16_batched(const PrismerBatchedGemmArgs* args, cudaStream_t stream);
+/* in place row softmax of bf16 scores [rows, ld] over the first Lk columns (padding columns are zeroed). */
+int prismer_softmax_rows(void* s, long long rows, int Lk, int ld, cudaStream_t stream);
+/* delta[(b*H+h)*Lq + q] = sum_d dO*O, tensors addressed as base + b*bs + q*rs + h*d. */
+int prismer_attn_delta(const void* dout, const void* o, long long bs, long long rs, float* delta, int B, int H, int Lq, int d,
+                       cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

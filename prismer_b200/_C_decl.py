@@ -33,6 +33,8 @@ SIGNATURES = {
     "prismer_conv_weight_unpack_grad": [P, P, I, I, I, I, P],
     "prismer_cast_pad": [P, P, L, I, I, P],
     "prismer_unpad_add": [P, P, L, I, I, P],
+    "prismer_softmax_rows": [P, L, I, I, P],
+    "prismer_attn_delta": [P, P, L, L, P, I, I, I, I, P],
 }
 
 

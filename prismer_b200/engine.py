@@ -525,6 +525,52 @@ def _pos_grad(vit, dtok_sf, B, n_tok, D, n_slots, slot_stride, interp):
 
 
 # ---------------------------------------------------------------------------------------------------- ViT block
+# EXPERIMENTAL (round-2 candidate, off by default, not yet validated on hardware): self-attention of the ViT blocks as batched
+# tcgen05 GEMMs over (batch, head) with the [B*H, S, S] probabilities kept for the backward (52 MB bf16 per layer at BASE,
+# L2-resident while in use).  Enable with PRISMER_ATTN_UNFUSED=1.
+import os as _os
+
+ATTN_UNFUSED = _os.environ.get("PRISMER_ATTN_UNFUSED") == "1"
+
+
+def _unfused_attn_fwd(qkv, o, B, S, H, save):
+    """qkv: [S*B, 3D] seq-first packed projections; o: [S*B, D] output buffer.  Returns P ([B*H, S, Sp] bf16) or None."""
+    D = o.shape[1]
+    d = D // H
+    Sp = (S + 7) // 8 * 8
+    P = torch.empty((B * H, S, Sp), dtype=BF16, device=qkv.device)
+    ld = B * 3 * D
+    qs = (3 * D, d)                                     # (outer = batch, inner = head) strides of the packed projections
+    ps = (H * S * Sp, S * Sp)
+    ops.gemm_batched(qkv, qkv[:, D:], P, S, S, d, lda=ld, ldb=ld, ldc=Sp, batch_outer=B, batch_inner=H, a_bs=qs, b_bs=qs, c_bs=ps,
+                     alpha=d ** -0.5)                   # scores = scale * Q K^T
+    ops.softmax_rows(P.view(B * H * S, Sp), S)
+    ops.gemm_batched(P, qkv[:, 2 * D:], o, S, d, S, lda=Sp, ldb=ld, ldc=B * D, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps,
+                     b_bs=qs, c_bs=(D, d))              # O = P V
+    return P if save else None
+
+
+def _unfused_attn_bwd(do, qkv, o, P, dqkv, B, S, H):
+    D = o.shape[1]
+    d = D // H
+    Sp = P.shape[2]
+    ld = B * 3 * D
+    qs, ps, os_ = (3 * D, d), (H * S * Sp, S * Sp), (D, d)
+    delta = ops.attn_delta(do, o, B, H, S, d)
+    # dV = P^T dO
+    ops.gemm_batched(P, do, dqkv[:, 2 * D:], S, d, S, lda=Sp, ldb=B * D, ldc=ld, trans_a=True, trans_b=True, batch_outer=B, batch_inner=H,
+                     a_bs=ps, b_bs=os_, c_bs=qs)
+    # dS = P * (dO V^T - delta) * scale   (softmax backward fused into the epilogue)
+    dS = torch.empty_like(P)
+    ops.gemm_batched(do, qkv[:, 2 * D:], dS, S, S, d, lda=B * D, ldb=ld, ldc=Sp, batch_outer=B, batch_inner=H, a_bs=os_, b_bs=qs, c_bs=ps,
+                     aux=P, ldaux=Sp, aux_bs=ps, rowvec=delta, rowvec_bs=S, mode=1, alpha=d ** -0.5)
+    # dQ = dS K ; dK = dS^T Q
+    ops.gemm_batched(dS, qkv[:, D:], dqkv, S, d, S, lda=Sp, ldb=ld, ldc=ld, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps, b_bs=qs,
+                     c_bs=qs)
+    ops.gemm_batched(dS, qkv, dqkv[:, D:], S, d, S, lda=Sp, ldb=ld, ldc=ld, trans_a=True, trans_b=True, batch_outer=B, batch_inner=H,
+                     a_bs=ps, b_bs=qs, c_bs=qs)
+
+
 def _vit_block_fwd(blk, adp, x, B, S, save):
     D, H = x.shape[1], blk.n_head
     at = blk.attn
@@ -532,7 +578,10 @@ def _vit_block_fwd(blk, adp, x, B, S, save):
     qkv = gemm(h, at.in_proj_weight._c16, bias=at.in_proj_bias.data)
     q3 = _sf(qkv, S, B)
     o = torch.empty((S * B, D), dtype=BF16, device=x.device)
-    _, lse = ops.attention_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], H, need_lse=save, out=_sf(o, S, B))
+    if ATTN_UNFUSED and D // H == 64:
+        lse = _unfused_attn_fwd(qkv, o, B, S, H, save)          # the saved probabilities take the place of the LSE
+    else:
+        _, lse = ops.attention_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], H, need_lse=save, out=_sf(o, S, B))
     x1 = gemm(o, at.out_proj.weight._c16, bias=at.out_proj.bias.data, residual=x)
     h2, mu2, rs2 = _ln(x1, adp.adaptor_ln, save)
     x2, (za, a) = _mlp_fwd(h2, adp.adaptor.down_proj, adp.adaptor.up_proj, "sqrelu", x1, save)
@@ -554,8 +603,11 @@ def _vit_block_bwd(blk, adp, dx3, sv, B, S):
     _lin_grads(dx1, sv.o, at.out_proj)
     dqkv = torch.empty_like(sv.qkv)
     q3, d3 = _sf(sv.qkv, S, B), _sf(dqkv, S, B)
-    ops.attention_bwd(_sf(do, S, B), q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], _sf(sv.o, S, B), sv.lse, H,
-                      dq=d3[..., :D], dk=d3[..., D:2 * D], dv=d3[..., 2 * D:])
+    if sv.lse is not None and sv.lse.dim() == 3 and sv.lse.dtype == BF16:      # experimental unfused path saved P
+        _unfused_attn_bwd(do, sv.qkv, sv.o, sv.lse, dqkv, B, S, H)
+    else:
+        ops.attention_bwd(_sf(do, S, B), q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], _sf(sv.o, S, B), sv.lse, H,
+                          dq=d3[..., :D], dk=d3[..., D:2 * D], dv=d3[..., 2 * D:])
     if at.in_proj_weight.requires_grad:
         _wgrad(dqkv, sv.h, at.in_proj_weight._g32)
         _bgrad(dqkv, at.in_proj_bias._g32)
