@@ -381,3 +381,81 @@ def rank_answers(enc, start_ids, start_mask, answer_ids, answer_mask, sd, heads,
     lps = (-loss / (targets != -100).sum(-1)).view(-1, k_test)
     mx = lps.argmax(1)
     return topk_ids[torch.arange(B), mx], topk_ids, lps
+
+
+def beam_generate(enc, input_ids, attention_mask, sd, heads, num_beams, max_length, min_length, length_penalty=1.0,
+                  eos=2, pad=1):
+    """Beam search as ``text_decoder.generate(num_beams=3, ...)`` runs it for prismer_caption.py:42-50 and
+    prismer_vqa.py:45-57 (cache-less decoder pass per step, roberta.py:401-406).
+
+    The search itself is third-party: ``transformers`` (reference pin ~=4.26.1, ``requirements.txt:6``; 5.5.0 in this
+    container).  This is a per-sample, list-based restatement of the 5.5.0 procedure -- the version the golden vectors
+    in tests/golden/prismer_tiny_beam.npz were produced with (oracle/gen_golden_beam.py):
+
+      every step : log_softmax of the last position -> MinLength (eos = -inf while cur_len < min_length) -> add the
+                   running beam scores -> the 2*num_beams best (beam, token) continuations of each sample;
+      a continuation "stops" when its token is eos or it reaches max_length;
+      running    : the num_beams best continuations that did not stop;
+      finished   : stopped continuations ranked inside the first num_beams candidates enter a pool of num_beams finished
+                   hypotheses with score sum_logprob / generated_len**length_penalty (generated_len counts the eos);
+      early stop : a sample is closed once its pool is full and its best running beam, normalised by the CURRENT generated
+                   length, can no longer beat the worst pooled score; the loop ends when every sample is closed or no
+                   continuation can be extended.
+
+    Returns (ids [B, L] padded with ``pad``, scores [B])."""
+    B, T0 = input_ids.shape
+    nb, K = num_beams, 2 * num_beams
+    enc_rep = enc.repeat_interleave(nb, dim=0)
+    run_seq = [[input_ids[b].tolist() for _ in range(nb)] for b in range(B)]
+    run_score = torch.zeros(B, nb)
+    run_score[:, 1:] = -1e9
+    pool_seq = [[input_ids[b].tolist() for _ in range(nb)] for b in range(B)]
+    pool_score = torch.full((B, nb), -1e9)
+    pool_done = torch.zeros(B, nb, dtype=torch.bool)
+    open_ = [True] * B
+    cur = T0
+    while True:
+        flat = torch.tensor([s for b in range(B) for s in run_seq[b]], dtype=torch.long)
+        att = torch.cat([attention_mask.repeat_interleave(nb, dim=0), torch.ones(B * nb, cur - T0, dtype=attention_mask.dtype)], 1)
+        logits, _ = decoder_forward(flat, att, enc_rep, sd, heads)
+        lp = torch.log_softmax(logits[:, -1].float(), dim=-1)
+        V = lp.shape[-1]
+        if cur < min_length:
+            lp[:, eos] = -float("inf")
+        acc = (lp.view(B, nb, V) + run_score[:, :, None]).reshape(B, nb * V)
+        top_s, top_i = acc.topk(K, dim=1)
+        can_extend = False
+        for b in range(B):
+            cands = [run_seq[b][int(i) // V] + [int(i) % V] for i in top_i[b]]
+            stop = torch.tensor([c[-1] == eos or cur + 1 >= max_length for c in cands])
+            can_extend = can_extend or not bool(stop.all())
+            # beams that keep running
+            alive = top_s[b] + stop.float() * -1.0e9
+            keep = alive.topk(nb).indices
+            run_seq[b] = [cands[int(j)] for j in keep]
+            run_score[b] = alive[keep]
+            # pool of finished hypotheses
+            fin = top_s[b] / ((cur + 1 - T0) ** length_penalty)
+            if not open_[b]:
+                fin = fin + -1.0e9
+            entered = stop & (torch.arange(K) < nb)
+            fin = fin + (~entered).float() * -1.0e9
+            m_score = torch.cat([pool_score[b], fin])
+            m_seq = pool_seq[b] + cands
+            m_done = torch.cat([pool_done[b], entered])
+            sel = m_score.topk(nb).indices
+            pool_score[b], pool_done[b] = m_score[sel], m_done[sel]
+            pool_seq[b] = [m_seq[int(j)] for j in sel]
+        cur += 1
+        for b in range(B):
+            best_running = run_score[b, 0] / ((cur - T0) ** length_penalty)
+            worst = pool_score[b].min() if bool(pool_done[b].all()) else torch.tensor(-1.0e9)
+            open_[b] = open_[b] and bool(best_running > worst)
+        if not (any(open_) and can_extend):
+            break
+    best = [pool_seq[b][0] for b in range(B)]
+    L = max(len(s) for s in best)
+    ids = torch.full((B, L), pad, dtype=torch.long)
+    for b, s in enumerate(best):
+        ids[b, :len(s)] = torch.tensor(s)
+    return ids, pool_score[:, 0].clone()

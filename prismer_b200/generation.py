@@ -12,7 +12,7 @@ import torch
 from . import engine, ops
 
 
-def _greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None):
+def _greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None, prompt_mask=None):
     """Device-side greedy loop on a preallocated ``ids`` [B, max_length] buffer (prefix already in columns [0, T0)).
     With ``early_exit=False`` there is no host synchronisation at all (finished rows keep emitting pad), so the whole loop
     can be captured in a CUDA graph."""
@@ -23,6 +23,8 @@ def _greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=No
     unfinished = torch.ones(B, dtype=torch.int64, device=dev)
     kv = engine.cross_kv(dec, enc)              # visual K/V of all layers: once per call, not once per step and layer
     ones = torch.ones((B, max_length), dtype=torch.int64, device=dev)
+    if prompt_mask is not None:                 # right-padded VQA questions (prismer_vqa.py:46-47); generated tokens attend
+        ones[:, :T0] = prompt_mask.to(torch.int64)
     cur = T0
     while cur < max_length:
         cur_ids = ids[:, :cur].contiguous()
@@ -47,7 +49,7 @@ def greedy(dec, input_ids, enc, attention_mask, max_length=20, min_length=0, ret
     ids = torch.full((B, max_length), dec.config.pad_token_id, dtype=torch.int64, device=input_ids.device)
     ids[:, :T0] = input_ids
     steps = [] if return_step_logits else None
-    cur = _greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit=True, steps=steps)
+    cur = _greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit=True, steps=steps, prompt_mask=attention_mask)
     out = ids[:, :cur]
     return (out, steps) if return_step_logits else out
 
@@ -119,66 +121,91 @@ class GraphedCaptioner:
         return self.ids
 
 
-@torch.no_grad()
-def beam_search(dec, input_ids, enc, attention_mask, num_beams, max_length, min_length, length_penalty=1.0):
-    """HF-style beam search (2*num_beams candidates, length-normalised scores).  Bookkeeping on the host; the decoder
-    passes and the log-softmax statistics run on the device."""
-    cfg = dec.config
-    eos, pad, V = cfg.eos_token_id, cfg.pad_token_id, cfg.vocab_size
-    engine._store(dec).refresh()
+def beam_search_core(step_logits, input_ids, attention_mask, num_beams, max_length, min_length, length_penalty, eos, pad):
+    """Batched beam search with all bookkeeping in fixed-shape device tensors (no per-hypothesis host objects): the
+    procedure ``text_decoder.generate(num_beams=3, ...)`` runs for prismer_caption.py:42-50 / prismer_vqa.py:45-57, i.e.
+    the ``transformers`` beam search (reference pin ~=4.26.1; the 5.5.0 procedure is the one that could be run and pinned
+    here -- tests/golden/prismer_tiny_beam.npz, oracle/gen_golden_beam.py).
+
+    ``step_logits(ids [B*nb, cur], mask [B*nb, cur]) -> [B*nb, V]`` fp32 logits of the last position.
+
+    State per sample: ``run_*`` the num_beams live beams, ``pool_*`` the num_beams best finished hypotheses (score =
+    sum_logprob / generated_len**length_penalty, eos counted), ``open_`` whether a live beam can still beat the pool.
+    One scalar is read back per step (loop exit test); everything else stays on the device.
+    Returns (ids [B, L] padded with ``pad``, scores [B])."""
     B, T0 = input_ids.shape
     dev = input_ids.device
-    nb = num_beams
-    enc_b = enc.repeat_interleave(nb, dim=0) if enc.is_contiguous() else enc.contiguous().repeat_interleave(nb, dim=0)
-    seqs = input_ids.repeat_interleave(nb, dim=0)
-    beam_scores = torch.zeros((B, nb), dtype=torch.float32, device=dev)
-    beam_scores[:, 1:] = -1e9
-    beam_scores = beam_scores.view(-1)
-    done = [False] * B
-    hyps = [[] for _ in range(B)]      # (score, tensor)
+    nb, K = num_beams, 2 * num_beams
+    f32 = torch.float32
+    run_seq = torch.full((B, nb, max_length), pad, dtype=torch.int64, device=dev)
+    run_seq[:, :, :T0] = input_ids[:, None, :]
+    pool_seq = run_seq.clone()
+    run_score = torch.zeros((B, nb), dtype=f32, device=dev)
+    run_score[:, 1:] = -1.0e9
+    pool_score = torch.full((B, nb), -1.0e9, dtype=f32, device=dev)
+    pool_done = torch.zeros((B, nb), dtype=torch.bool, device=dev)
+    pool_len = torch.full((B, nb), T0, dtype=torch.int64, device=dev)
+    open_ = torch.ones((B, 1), dtype=torch.bool, device=dev)
+    in_top = (torch.arange(K, device=dev) < nb)[None, :]
+    mask = torch.ones((B * nb, max_length), dtype=torch.int64, device=dev)
+    if attention_mask is not None:
+        mask[:, :T0] = attention_mask.to(torch.int64).repeat_interleave(nb, dim=0)
+    take = lambda t, idx: t.gather(1, idx[:, :, None].expand(-1, -1, t.shape[2]))
     cur = T0
     while cur < max_length:
-        logits, _, _, _ = engine.decoder_forward(dec, seqs.contiguous(), torch.ones_like(seqs), enc_b, None, None, save=False)
-        last = logits.view(B * nb, cur, -1)[:, -1].float()
-        lp = last - torch.logsumexp(last, dim=-1, keepdim=True)
+        logits = step_logits(run_seq[:, :, :cur].reshape(B * nb, cur), mask[:, :cur])
+        lp = torch.log_softmax(logits.to(f32), dim=-1)
+        V = lp.shape[-1]
         if cur < min_length:
-            lp[:, eos] = -float("inf")
-        scores = (lp + beam_scores[:, None]).view(B, nb * V)
-        top_s, top_i = scores.topk(2 * nb, dim=1)
-        top_s, top_i = top_s.cpu(), top_i.cpu()
-        new_seqs, new_scores = [], []
-        for b in range(B):
-            cand = []
-            for s, i in zip(top_s[b].tolist(), top_i[b].tolist()):
-                beam, tok = i // V, i % V
-                if tok == eos:
-                    if len(cand) < nb and not done[b]:
-                        hyps[b].append((s / ((cur + 1 - 0) ** length_penalty), seqs[b * nb + beam].clone()))
-                    continue
-                cand.append((s, beam, tok))
-                if len(cand) == nb:
-                    break
-            if len(hyps[b]) >= nb:
-                best_possible = cand[0][0] / ((cur + 1) ** length_penalty) if cand else -1e30
-                worst = sorted(h[0] for h in hyps[b])[-nb]
-                done[b] = done[b] or worst >= best_possible
-            for s, beam, tok in cand:
-                new_seqs.append(torch.cat([seqs[b * nb + beam], torch.tensor([tok], device=dev)]))
-                new_scores.append(s)
-        seqs = torch.stack(new_seqs)
-        beam_scores = torch.tensor(new_scores, dtype=torch.float32, device=dev)
+            lp[:, eos] = -float("inf")                      # MinLengthLogitsProcessor
+        acc = (lp.view(B, nb, V) + run_score[:, :, None]).view(B, nb * V)
+        top_s, top_i = acc.topk(K, dim=1)                   # 2*nb continuations: enough live ones survive nb eos hits
+        cand = take(run_seq, top_i // V)
+        tok = top_i % V
+        cand[:, :, cur] = tok
+        stop = (tok == eos) | (cur + 1 >= max_length)
+        # live beams of the next step
+        alive = top_s + stop.to(f32) * -1.0e9
+        keep = alive.topk(nb, dim=1).indices
+        run_seq, run_score = take(cand, keep), alive.gather(1, keep)
+        # finished pool: only stopped continuations ranked inside the first nb, and only while the sample is open
+        entered = stop & in_top
+        fin = top_s / ((cur + 1 - T0) ** length_penalty)
+        fin = fin + (~open_).to(f32) * -1.0e9
+        fin = fin + (~entered).to(f32) * -1.0e9
+        m_score = torch.cat([pool_score, fin], dim=1)
+        sel = m_score.topk(nb, dim=1).indices
+        pool_score = m_score.gather(1, sel)
+        pool_seq = take(torch.cat([pool_seq, cand], dim=1), sel)
+        pool_done = torch.cat([pool_done, entered], dim=1).gather(1, sel)
+        pool_len = torch.cat([pool_len, torch.full((B, K), cur + 1, dtype=torch.int64, device=dev)], dim=1).gather(1, sel)
         cur += 1
-        if all(done):
+        # can the best live beam (normalised by the current generated length) still beat the worst pooled hypothesis?
+        best_running = run_score[:, :1] / ((cur - T0) ** length_penalty)
+        worst = torch.where(pool_done, pool_score.min(dim=1, keepdim=True).values, torch.full_like(pool_score, -1.0e9))
+        open_ = open_ & (best_running > worst).any(dim=1, keepdim=True)
+        if not bool(open_.any() & ~stop.all()):
             break
-    out = []
-    for b in range(B):
-        if not done[b] or len(hyps[b]) < 1:
-            for k in range(nb):
-                hyps[b].append((float(beam_scores[b * nb + k]) / (cur ** length_penalty), seqs[b * nb + k]))
-        best = max(hyps[b], key=lambda h: h[0])[1]
-        out.append(best)
-    L = max(len(o) for o in out)
-    res = torch.full((B, L), pad, dtype=torch.int64, device=dev)
-    for b, o in enumerate(out):
-        res[b, :len(o)] = o
-    return res
+    L = int(pool_len[:, 0].max())
+    return pool_seq[:, 0, :L].contiguous(), pool_score[:, 0].contiguous()
+
+
+@torch.no_grad()
+def beam_search(dec, input_ids, enc, attention_mask, num_beams, max_length, min_length, length_penalty=1.0, return_scores=False):
+    """``generate(num_beams>1)``: ``beam_search_core`` driven by the CUDA decoder.  Like the reference's cache-less
+    ``prepare_inputs_for_generation`` (roberta.py:401-406) every step re-runs the decoder on the full prefix; the
+    cross-attention K/V of the (beam-expanded, prismer_caption.py:45 via ``_expand_inputs_for_generation``) visual tokens are
+    projected once per call and only the last position goes through the LM head."""
+    cfg = dec.config
+    engine._store(dec).refresh()
+    enc_b = enc.contiguous().repeat_interleave(num_beams, dim=0)
+    kv = engine.cross_kv(dec, enc_b)
+
+    def step_logits(ids, mask):
+        last, _, _, _ = engine.decoder_forward(dec, ids.contiguous(), mask.contiguous(), enc_b, None, None, save=False, kv=kv,
+                                               last_only=True)
+        return last
+
+    ids, scores = beam_search_core(step_logits, input_ids, attention_mask, num_beams, max_length, min_length, length_penalty,
+                                   cfg.eos_token_id, cfg.pad_token_id)
+    return (ids, scores) if return_scores else ids

@@ -53,3 +53,55 @@ def build_model(width, layers, patch, res, experts, dec_cfg, seed, device="cuda"
             p.requires_grad = not ("transformer.resblocks" in n and "adaptor" not in n)
     m.to(device)
     return m, sd
+
+
+# ------------------------------------------------------------------------------------------------ beam-search fixtures
+# Cases of tests/golden/prismer_tiny_beam.npz (made by oracle/gen_golden_beam.py from the reference decoder).  ``boost`` is
+# added to the LM-head eos bias so that hypotheses finish at different lengths; lengths are relative to the prompt length T0.
+BEAM_SEED = 21
+BEAM_CASES = [
+    dict(name="cap_a", B=4, T0=4, ragged=False, S=20, boost=1.5, nb=3, max_add=16, min_add=4, lp=1.0),
+    dict(name="cap_b", B=4, T0=4, ragged=False, S=20, boost=2.0, nb=3, max_add=16, min_add=4, lp=1.0),
+    dict(name="cap_c", B=3, T0=4, ragged=False, S=12, boost=2.5, nb=3, max_add=16, min_add=4, lp=1.0),
+    dict(name="cap_d", B=2, T0=4, ragged=False, S=12, boost=2.0, nb=4, max_add=12, min_add=0, lp=2.0),
+    dict(name="cap_e", B=3, T0=4, ragged=False, S=12, boost=0.0, nb=3, max_add=8, min_add=4, lp=1.0),      # nothing finishes early
+    dict(name="vqa_a", B=4, T0=7, ragged=True, S=20, boost=2.0, nb=3, max_add=10, min_add=2, lp=-1.0),
+    dict(name="vqa_b", B=3, T0=6, ragged=True, S=12, boost=1.0, nb=3, max_add=10, min_add=2, lp=-1.0),
+]
+
+
+def beam_decoder_state(template, boost):
+    """Decoder state_dict (keys without the ``text_decoder.`` prefix) for a beam case: seeded fill + eos-bias boost."""
+    sd = synthetic.synth_state_dict({"text_decoder." + k: v for k, v in template.items()}, BEAM_SEED)
+    sd = {k[len("text_decoder."):]: v for k, v in sd.items()}
+    sd["lm_head.bias"] = sd["lm_head.bias"].clone()
+    sd["lm_head.bias"][TINY_DEC["eos_token_id"]] += boost
+    sd["lm_head.decoder.bias"] = sd["lm_head.bias"]
+    return sd
+
+
+def beam_case_inputs(c):
+    """(prompt ids, prompt mask, visual tokens [B, S, Dv]) of a beam case."""
+    ids, mask = synthetic.synth_tokens(c["B"], c["T0"] + 1, TINY_DEC["vocab_size"], BEAM_SEED + len(c["name"]) + c["B"],
+                                       ragged=c["ragged"])
+    if c["ragged"]:                                       # VQA: `<s> question </s>` right-padded (prismer_vqa.py:19,46-47)
+        ids, mask = ids[:, :c["T0"]].clone(), mask[:, :c["T0"]].clone()
+        ids[:, 0] = 0
+    else:                                                 # caption: one prefix for every row, `</s>` dropped (prismer_caption.py:38-40)
+        ids = ids[:1, :c["T0"]].repeat(c["B"], 1)
+        ids[ids == 2] = 7
+        mask = torch.ones_like(ids)
+    rs = np.random.RandomState(BEAM_SEED * 1000 + sum(map(ord, c["name"])))      # O(1) visual tokens, like ln_post output
+    enc = torch.from_numpy(rs.standard_normal((c["B"], c["S"], TINY_DEC["vision_hidden_size"])).astype(np.float32))
+    return ids, mask, enc
+
+
+def load_beam_golden():
+    z = np.load(os.path.join(GOLD, "prismer_tiny_beam.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def decoder_template():
+    from prismer_b200.modeling import template_state_dict
+    t = template_state_dict(width=256, layers=2, patch=16, res=64, experts=[], dec_cfg=TINY_DEC)
+    return {k[len("text_decoder."):]: v for k, v in t.items() if k.startswith("text_decoder.")}

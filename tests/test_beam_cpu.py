@@ -1,0 +1,68 @@
+"""Beam search (prismer_caption.py:42-50, prismer_vqa.py:45-57) without a GPU:
+
+  * the oracle restatement ``oracle.prismer_oracle.beam_generate`` is pinned against golden ids + sequence scores that
+    ``oracle/gen_golden_beam.py`` produced with the UNMODIFIED reference decoder under ``transformers.generate``;
+  * the product's fixed-shape bookkeeping ``prismer_b200.generation.beam_search_core`` is run on CPU tensors with the oracle
+    decoder supplying the per-step logits, and must return the same ids bit-exactly -- so on the GPU only the logits differ.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import prismer_oracle as O
+from prismer_b200 import generation
+from tests.helpers import (BEAM_CASES, TINY_DEC, beam_case_inputs, beam_decoder_state, decoder_template, load_beam_golden)
+
+HEADS = TINY_DEC["num_attention_heads"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_beam_golden()
+
+
+@pytest.fixture(scope="module")
+def template():
+    return decoder_template()
+
+
+def _case(c, template, gold):
+    sd = beam_decoder_state(template, c["boost"])
+    ids, mask, enc = beam_case_inputs(c)
+    assert np.array_equal(ids.numpy(), gold[c["name"] + ".prompt"]) and np.array_equal(mask.numpy(), gold[c["name"] + ".mask"])
+    return sd, ids, mask, enc
+
+
+@pytest.mark.parametrize("c", BEAM_CASES, ids=[c["name"] for c in BEAM_CASES])
+def test_oracle_beam_matches_reference(c, template, gold):
+    sd, ids, mask, enc = _case(c, template, gold)
+    with torch.no_grad():
+        out, sc = O.beam_generate(enc, ids, mask, sd, HEADS, c["nb"], c["T0"] + c["max_add"], c["T0"] + c["min_add"], c["lp"])
+    assert np.array_equal(out.numpy(), gold[c["name"] + ".ids"])            # token ids: bit-exact
+    np.testing.assert_allclose(sc.numpy(), gold[c["name"] + ".scores"], rtol=2e-6, atol=2e-5)
+
+
+@pytest.mark.parametrize("c", BEAM_CASES, ids=[c["name"] for c in BEAM_CASES])
+def test_product_bookkeeping_matches_reference(c, template, gold):
+    sd, ids, mask, enc = _case(c, template, gold)
+    enc_b = enc.repeat_interleave(c["nb"], dim=0)
+
+    def step_logits(flat_ids, flat_mask):
+        logits, _ = O.decoder_forward(flat_ids, flat_mask, enc_b, sd, HEADS)
+        return logits[:, -1].float()
+
+    with torch.no_grad():
+        out, sc = generation.beam_search_core(step_logits, ids, mask, c["nb"], c["T0"] + c["max_add"], c["T0"] + c["min_add"],
+                                              c["lp"], TINY_DEC["eos_token_id"], TINY_DEC["pad_token_id"])
+    assert np.array_equal(out.numpy(), gold[c["name"] + ".ids"])
+    np.testing.assert_allclose(sc.numpy(), gold[c["name"] + ".scores"], rtol=2e-6, atol=2e-5)
+
+
+def test_beam_core_without_prompt_mask_equals_all_ones(template, gold):
+    c = BEAM_CASES[1]
+    sd, ids, mask, enc = _case(c, template, gold)
+    enc_b = enc.repeat_interleave(c["nb"], dim=0)
+    step = lambda i, m: O.decoder_forward(i, m, enc_b, sd, HEADS)[0][:, -1].float()
+    with torch.no_grad():
+        out, _ = generation.beam_search_core(step, ids, None, c["nb"], c["T0"] + c["max_add"], c["T0"] + c["min_add"], c["lp"], 2, 1)
+    assert np.array_equal(out.numpy(), gold[c["name"] + ".ids"])
