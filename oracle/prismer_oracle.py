@@ -459,3 +459,51 @@ def beam_generate(enc, input_ids, attention_mask, sd, heads, num_beams, max_leng
     for b, s in enumerate(best):
         ids[b, :len(s)] = torch.tensor(s)
     return ids, pool_score[:, 0].clone()
+
+
+# ---------------------------------------------------------------------------------------------------- model-level glue
+def _encode(experts, sd, patch_size, rng):
+    esd, dsd = split_state_dict(sd)
+    return encoder_forward(experts, esd, patch_size, rng=rng).transpose(0, 1), dsd
+
+
+def caption_forward(experts, sd, tokenizer, patch_size, heads, caption=None, answer=None, train=True, prefix="",
+                    inference="generate", k_test=32, rng=random):
+    """PrismerCaption.forward (prismer_caption.py:15-112) on strings; eval-mode modules (no dropout, BN running stats)."""
+    enc, dsd = _encode(experts, sd, patch_size, rng)
+    B = enc.shape[0]
+    if train:                                                                    # :17-34
+        tok = tokenizer(caption, padding="longest", truncation=True, max_length=30, return_tensors="pt")
+        prompt = len(tokenizer(prefix).input_ids) - 1 if len(prefix) > 0 else 0
+        labels = caption_labels(tok.input_ids, prompt, tokenizer.pad_token_id)
+        _, loss = decoder_forward(tok.input_ids, tok.attention_mask, enc, dsd, heads, labels)
+        return loss.mean()
+    ptok = tokenizer([prefix] * B, padding="longest", return_tensors="pt")
+    start_ids, start_mask = ptok.input_ids[:, :-1], ptok.attention_mask[:, :-1]  # :38-40, :70-71 (drop </s>)
+    if inference == "generate":                                                  # :36-57
+        ids, _ = beam_generate(enc, start_ids, start_mask, dsd, heads, 3, 20, 8)
+        cut = len(prefix) + (1 if len(prefix) > 0 else 0)
+        return [tokenizer.decode(row, skip_special_tokens=True)[cut:] for row in ids]
+    atok = tokenizer([" " + a.lower() + "</s>" for a in answer], padding="longest", return_tensors="pt", add_special_tokens=False)
+    return rank_answers(enc, start_ids, start_mask, atok.input_ids, atok.attention_mask, dsd, heads, k_test, tokenizer.pad_token_id)[0]
+
+
+def vqa_forward(experts, sd, tokenizer, patch_size, heads, question, answer=None, weights=None, train=True, inference="rank",
+                k_test=128, rng=random):
+    """PrismerVQA.forward (prismer_vqa.py:16-113) on strings; eval-mode modules."""
+    enc, dsd = _encode(experts, sd, patch_size, rng)
+    q = tokenizer(["<s>" + s.capitalize() for s in question], padding="longest", truncation=True, max_length=35,
+                  add_special_tokens=False, return_tensors="pt")                   # :18-20
+    if not train and inference == "generate":                                     # :44-62
+        T0 = q.input_ids.shape[1]
+        ids, _ = beam_generate(enc, q.input_ids, q.attention_mask, dsd, heads, 3, T0 + 10, T0 + 2, length_penalty=-1)
+        return [tokenizer.decode(row[T0:], skip_special_tokens=True).lower().strip() for row in ids]
+    a = tokenizer([" " + s.capitalize() + "</s>" for s in answer], padding="longest", return_tensors="pt", add_special_tokens=False)
+    if train:                                                                     # :22-42
+        ids = torch.cat([q.input_ids, a.input_ids], 1).long()
+        att = torch.cat([q.attention_mask, a.attention_mask], 1)
+        targets = ids.masked_fill(ids == tokenizer.pad_token_id, -100)
+        targets[:, :-a.input_ids.shape[1]] = -100
+        _, loss = decoder_forward(ids, att, enc, dsd, heads, targets)
+        return (weights * loss).mean()
+    return rank_answers(enc, q.input_ids, q.attention_mask, a.input_ids, a.attention_mask, dsd, heads, k_test, tokenizer.pad_token_id)[0]

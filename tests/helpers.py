@@ -105,3 +105,19 @@ def decoder_template():
     from prismer_b200.modeling import template_state_dict
     t = template_state_dict(width=256, layers=2, patch=16, res=64, experts=[], dec_cfg=TINY_DEC)
     return {k[len("text_decoder."):]: v for k, v in t.items() if k.startswith("text_decoder.")}
+
+
+# ------------------------------------------------------------------------------------------------ model-level (string API) fixture
+# Inputs of tests/golden/prismer_tiny_surface.npz (oracle/gen_golden_surface.py: the reference's own PrismerCaption / PrismerVQA
+# ``forward`` on the fixture-A modules with the HashTokenizer stand-in).
+SURFACE = dict(
+    cfg=dict(width=256, layers=2, patch=16, res=64, label=64, B=2, seed=7, in_seed=11, py_seed=1234),
+    prefix="A picture of",
+    captions=["A picture of a dog sleeping on a red couch", "A picture of two people riding bikes"],
+    classes=["dog", "cat", "traffic light", "people", "a couch in a room"],
+    questions=["what is the animal doing", "how many people are there in the picture"],
+    answers=["sleeping", "two people"],
+    weights=[0.5, 1.0],
+    candidates=["sleeping", "running fast", "two people", "no", "yes it is", "a dog"],
+    k_test=3,
+)
