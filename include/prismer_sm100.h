@@ -197,6 +197,21 @@ int prismer_cast_pad(const float* src, void* dst, long long R, int C, int Cpad, 
 int prismer_unpad_add(const float* src, float* dst, long long R, int C, int Cpad, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Compact expert inputs: every expert map of dataset/utils.py:117-160 (post_label_process) is a uint8 image
+ * pushed through a <= 256-row table (label id -> 64-d CLIP feature row, 255 = background; or grey level -> min/max-remapped
+ * value).  The host ships the uint8 map + table (50 KB instead of 12.8 MB per modality and image); the expansion runs here.
+ *   labels: uint8 [B, Cin, H*W];  table: fp32 [*, 256, C], per-image stride table_bs elements (0 = one shared table).
+ *   prismer_expand_labels : out fp32 NCHW [B, Cin*C, H*W], out[b, ci*C+c, p] = table[b][labels[b,ci,p]][c]  (the tensor the
+ *                           reference's workers build, dataset/utils.py:120-158)
+ *   prismer_label_resample: Cin = 1; out bf16 NHWC [B, Ho, Wo, C] = UpsamplingBilinear2d(align_corners=True) of that tensor
+ *                           (vit.py:89) without materialising it; bit-identical to prismer_resample_bilinear on the expansion.
+ * --------------------------------------------------------------------------------------------------------- */
+int prismer_expand_labels(const void* labels, const float* table, long long table_bs, float* out, int B, int Cin, long long HW,
+                          int C, cudaStream_t stream);
+int prismer_label_resample(const void* labels, const float* table, long long table_bs, void* out, int B, int C, int Hi, int Wi,
+                           int Ho, int Wo, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * EXPERIMENTAL (round-2 candidate; compiled and exported but not on the default path and not yet validated on hardware):
  * attention as batched tcgen05 GEMMs over (batch, head) problems with L2-resident score matrices.
  *   C_i[M,N] = epilogue(alpha * op(A_i) . op(B_i)^T),  X_i = X + bo * X_bs_outer + bi * X_bs_inner (elements)

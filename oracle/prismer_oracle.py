@@ -507,3 +507,36 @@ def vqa_forward(experts, sd, tokenizer, patch_size, heads, question, answer=None
         _, loss = decoder_forward(ids, att, enc, dsd, heads, targets)
         return (weights * loss).mean()
     return rank_answers(enc, q.input_ids, q.attention_mask, a.input_ids, a.attention_mask, dsd, heads, k_test, tokenizer.pad_token_id)[0]
+
+
+# ---------------------------------------------------------------------------------------------------- expert-label post-processing
+def post_label_process(inputs, labels_info, features, eps=1e-6):
+    """dataset/utils.py:117-160 restated with numpy-style indexing.  ``inputs``: what ``Transform`` returns (:56-63) --
+    float [c,H,W] in [0,1] for depth / normal / edge, int64 [1,H,W] label maps otherwise.  ``features``: the tables the
+    reference loads as module globals (:17-20): {'coco','ade','detection': [N,64], 'background': [64]}."""
+    out = {}
+    for exp, x in inputs.items():
+        if exp in ("depth", "normal", "edge"):                       # :120-121  remap to [-1, 1] with the per-sample range
+            out[exp] = 2 * (x - x.min()) / (x.max() - x.min() + eps) - 1
+            continue
+        if exp == "rgb":
+            out[exp] = x
+            continue
+        ids = x[0]
+        emb = torch.empty((64, *ids.shape), dtype=torch.float32)
+        for l in torch.unique(ids).tolist():
+            if l == 255:
+                row = features["background"]                          # :126,135,145,155
+            elif exp == "seg_coco":
+                row = features["coco"][l]                             # :128
+            elif exp == "seg_ade":
+                row = features["ade"][l]                              # :137
+            elif exp == "obj_detection":
+                row = features["detection"][labels_info[exp][str(l)]]  # :147 (json keys are strings)
+            elif exp == "ocr_detection":
+                row = labels_info[exp][l]["features"]                 # :157
+            else:
+                raise KeyError(exp)
+            emb[:, ids == l] = row[:, None]
+        out[exp] = {"label": emb, "instance": x} if exp == "obj_detection" else emb   # :148
+    return out

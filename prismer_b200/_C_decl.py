@@ -25,6 +25,8 @@ SIGNATURES = {
     "prismer_argmax": [P, L, I, I, I, I, P, P],
     "prismer_patchify": [P, P, I, I, I, I, I, P],
     "prismer_resample_bilinear": [P, P, I, I, I, I, I, I, P],
+    "prismer_expand_labels": [P, P, L, P, I, I, L, I, P],
+    "prismer_label_resample": [P, P, L, P, I, I, I, I, I, I, P],
     "prismer_im2col_first": [P, I, L, L, L, L, P, I, I, I, I, I, I, I, I, I, P],
     "prismer_im2col_nhwc": [P, P, P, P, I, I, I, I, I, I, I, I, P],
     "prismer_bn_stats": [P, P, L, I, P, P, P, P, P, P, P, P, F, F, I, P],

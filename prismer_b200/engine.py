@@ -24,6 +24,7 @@ import torch.nn as nn
 
 from . import ops
 from .ops import BF16, F32, gemm
+from .data import CompactMap
 
 # dropout call-site ids (Philox streams)
 _RS_EMB, _RS_SELF_P, _RS_SELF_O, _RS_CROSS_P, _RS_CROSS_O, _RS_MLP_O = 1, 2, 3, 4, 5, 6
@@ -318,13 +319,19 @@ def _conv_out(h, s):
 
 
 def _stem_fwd(stem, x, training: bool, save: bool):
+    """``x``: the reference's fp32 NCHW expert tensor, or a ``CompactMap`` (uint8 map + table, data.py) standing for it."""
+    compact = isinstance(x, CompactMap)
     B, Cin, Hl, Wl = x.shape
     sf = stem.scale_factor
     if sf != 1.0:
         H, W = int(math.floor(Hl * sf)), int(math.floor(Wl * sf))
-        cur, nhwc = ops.resample_bilinear(x, H, W), True
+        if compact and x.u8.shape[1] == 1 and Cin % 8 == 0:
+            cur = ops.label_resample(x.u8, x.table, H, W)       # in-painting fused into the resample: never materialised
+        else:
+            cur = ops.resample_bilinear(x.expand() if compact else x, H, W)
+        nhwc = True
     else:
-        H, W, cur, nhwc = Hl, Wl, x, False
+        H, W, cur, nhwc = Hl, Wl, (x.expand() if compact else x), False
     C = Cin
     layers = []
     scale = shift = None
@@ -445,7 +452,9 @@ def encoder_forward(vit, experts: Dict, save: bool, inst_table: Optional[torch.T
             pos_e, interp = _pos_for(vit, n_e, save)
             inst = table = None
             if e == "obj_detection":
-                inst = experts[e]["instance"]
+                inst = experts[e].get("instance")
+                if inst is None:                         # compact input: the label map IS the instance map (dataset/utils.py:146)
+                    inst = experts[e]["label"].u8.long()
                 table = inst_table if inst_table is not None else _instance_table(inst)
             ops.assemble_tokens(t, pos_e, xf[off * B:], D, B * D, B, n_e, D, gh, gw, inst, table,
                                 vit.instance_embedding._c16 if inst is not None else None)
@@ -917,7 +926,7 @@ def _experts_check(experts):
     for k, v in experts.items():
         ts = v.values() if isinstance(v, dict) else [v]
         for t in ts:
-            if not t.is_cuda:
+            if t is not None and not (t.u8 if isinstance(t, CompactMap) else t).is_cuda:
                 raise ops._C.PrismerError("prismer_b200 runs on CUDA tensors only (no CPU fallback): move the experts dict to the GPU")
 
 
@@ -925,8 +934,7 @@ def encoder_apply(vit, experts: Dict) -> torch.Tensor:
     """``VisionTransformer.forward``: inference-style call (no autograd graph); returns [S, B, D] bf16."""
     _experts_check(experts)
     _store(vit).refresh()
-    experts = {k: ({kk: vv.contiguous() for kk, vv in v.items()} if isinstance(v, dict) else v.float().contiguous())
-               for k, v in experts.items()}
+    experts = _canon_experts(experts)
     out, S, B, _ = encoder_forward(vit, experts, save=False)
     return out.view(S, B, -1)
 
@@ -994,9 +1002,16 @@ def _backward_train(model, esv, dsv, gscale):
     _backward_encoder(model, esv, denc)
 
 
+def _canon_one(v, top: bool):
+    if isinstance(v, CompactMap):
+        return CompactMap(v.u8.contiguous(), v.table.contiguous())
+    if isinstance(v, dict):
+        return {kk: _canon_one(vv, False) for kk, vv in v.items() if vv is not None}
+    return v.float().contiguous() if top else v.contiguous()
+
+
 def _canon_experts(experts):
-    return {k: ({kk: vv.contiguous() for kk, vv in v.items()} if isinstance(v, dict) else v.float().contiguous())
-            for k, v in experts.items()}
+    return {k: _canon_one(v, True) for k, v in experts.items()}
 
 
 class GraphedTrainStep:
@@ -1092,6 +1107,5 @@ def train_loss(model, experts, input_ids, attention_mask, labels, weights=None) 
     _experts_check(experts)
     st = _store(model)
     anchor = st.train_params[0] if st.train_params else torch.zeros((), device=st.device, requires_grad=True)
-    experts = {k: ({kk: vv.contiguous() for kk, vv in v.items()} if isinstance(v, dict) else v.float().contiguous())
-               for k, v in experts.items()}
+    experts = _canon_experts(experts)
     return _TrainStep.apply(anchor, model, experts, input_ids, attention_mask, labels, weights)

@@ -321,6 +321,37 @@ def resample_bilinear(x, Ho, Wo):
     return out
 
 
+def _table_stride(table, B):
+    """table: fp32 [256, C] (shared) or [B, 256, C] (per image) -> element stride between images."""
+    assert table.dtype == F32 and table.is_contiguous() and table.shape[-2] == 256
+    if table.dim() == 2:
+        return 0
+    assert table.shape[0] == B
+    return table.shape[1] * table.shape[2]
+
+
+def expand_labels(u8, table):
+    """uint8 [B, Cin, H, W] through fp32 table [256, C] / [B, 256, C] -> fp32 NCHW [B, Cin*C, H, W] (dataset/utils.py:117-160)."""
+    assert u8.dtype == torch.uint8 and u8.is_contiguous() and u8.dim() == 4
+    B, Cin, H, W = u8.shape
+    C = table.shape[-1]
+    out = torch.empty((B, Cin * C, H, W), dtype=F32, device=u8.device)
+    check(_C.lib().prismer_expand_labels(u8.data_ptr(), table.data_ptr(), _table_stride(table, B), out.data_ptr(), B, Cin, H * W, C,
+                                         _stream()), "expand_labels")
+    return out
+
+
+def label_resample(u8, table, Ho, Wo):
+    """uint8 [B, 1, H, W] label map + table -> bf16 NHWC [B, Ho, Wo, C]: in-painting fused with UpsamplingBilinear2d (vit.py:89)."""
+    assert u8.dtype == torch.uint8 and u8.is_contiguous() and u8.dim() == 4 and u8.shape[1] == 1
+    B, _, Hi, Wi = u8.shape
+    C = table.shape[-1]
+    out = torch.empty((B, Ho, Wo, C), dtype=BF16, device=u8.device)
+    check(_C.lib().prismer_label_resample(u8.data_ptr(), table.data_ptr(), _table_stride(table, B), out.data_ptr(), B, C, Hi, Wi, Ho, Wo,
+                                          _stream()), "label_resample")
+    return out
+
+
 def im2col_first(x, nhwc_bf16: bool, B, Cin, H, W, ksz, stride, Kpad):
     Ho, Wo = (H + 2 * (ksz // 2) - ksz) // stride + 1, (W + 2 * (ksz // 2) - ksz) // stride + 1
     out = torch.empty((B * Ho * Wo, Kpad), dtype=BF16, device=x.device)

@@ -143,3 +143,52 @@ def experts_to(experts: Dict, device, non_blocking: bool = False, dtype=None) ->
         else:
             out[k] = v.to(device, non_blocking=non_blocking)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ compact expert inputs
+def synth_features(seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Stand-ins for dataset/{coco,ade,detection,background}_features.pt (CLIP-PCA rows: mean -0.06, std 0.75)."""
+    rs = _rs(seed, "features")
+    f = lambda n: torch.from_numpy((-0.06 + 0.75 * rs.standard_normal((n, 64))).astype(np.float32))
+    return {"coco": f(133), "ade": f(150), "detection": f(722), "background": f(1)[0]}
+
+
+def synth_compact_experts(batch: int, image_resolution: int = 224, experts: Iterable[str] = DEFAULT_EXPERTS,
+                          label_size: int = 224, seed: int = 0) -> Dict:
+    """The same pipeline as the reference's workers, in the compact format: per-sample uint8 maps ->
+    ``data.compact_label_process`` (drop-in for dataset/utils.py:117-160) -> ``data.collate_experts``."""
+    from . import data
+    feats = synth_features(seed)
+    samples = []
+    for b in range(batch):
+        rs = _rs(seed, f"compact.{b}")
+        s = OrderedDict(rgb=torch.from_numpy(rs.standard_normal((3, image_resolution, image_resolution)).astype(np.float32)))
+        info = {}
+        for e in experts:
+            if e in ("depth", "edge", "normal"):
+                s[e] = torch.from_numpy(rs.randint(0, 256, (EXPERT_CHANNELS[e], label_size, label_size)).astype(np.uint8))
+                continue
+            n = {"seg_coco": 133, "seg_ade": 150, "obj_detection": 5, "ocr_detection": 3}[e]
+            m = _blocky(rs, 1, label_size, 7, n)
+            m = np.where(_blocky(rs, 1, label_size, 5, 4) == 0, 255, m).astype(np.uint8)
+            s[e] = torch.from_numpy(m)
+            if e == "obj_detection":
+                info[e] = {str(i): int(rs.randint(0, 722)) for i in range(n)}
+            elif e == "ocr_detection":
+                info[e] = {i: {"features": torch.from_numpy((0.75 * rs.standard_normal(64)).astype(np.float32))} for i in range(n)}
+        samples.append(data.compact_label_process(s, info, feats))
+    return data.collate_experts(samples)
+
+
+def expand_compact_on_host(experts: Dict) -> Dict:
+    """The float ``experts`` dict the reference's workers would have produced for a compact one (host tensors)."""
+    from . import data
+    out = OrderedDict()
+    for k, v in experts.items():
+        if isinstance(v, data.CompactMap):
+            out[k] = v.expand_on_host()
+        elif isinstance(v, dict):
+            out[k] = {kk: (vv.expand_on_host() if isinstance(vv, data.CompactMap) else vv) for kk, vv in v.items()}
+        else:
+            out[k] = v
+    return out

@@ -121,3 +121,31 @@ SURFACE = dict(
     candidates=["sleeping", "running fast", "two people", "no", "yes it is", "a dog"],
     k_test=3,
 )
+
+
+# ------------------------------------------------------------------------------------------------ expert-label fixtures
+def label_case(case: int, size: int = 24):
+    """Seeded uint8 expert maps of one sample + the ``labels_info`` side data (dataset/utils.py:98-110) for
+    tests/golden/prismer_labels.npz.  Case 2 has a constant depth map (max == min) and an all-background ocr map."""
+    rs = np.random.RandomState(100 + case)
+    u8 = {}
+    u8["depth"] = torch.from_numpy(rs.randint(3, 250, (1, size, size)).astype(np.uint8))
+    u8["normal"] = torch.from_numpy(rs.randint(0, 256, (3, size, size)).astype(np.uint8))
+    u8["edge"] = torch.from_numpy(rs.randint(0, 120, (1, size, size)).astype(np.uint8))
+    if case == 2:
+        u8["depth"][:] = 77
+    def ids(n, cells, bg_frac):
+        m = synthetic._blocky(rs, 1, size, cells, n).astype(np.int64)
+        m[rs.uniform(size=m.shape) < bg_frac] = 255
+        return torch.from_numpy(m.astype(np.uint8))
+    u8["seg_coco"] = torch.from_numpy(np.where(rs.uniform(size=(1, size, size)) < 0.2, 255,
+                                               synthetic._blocky(rs, 1, size, 5, 133)).astype(np.uint8))
+    u8["seg_ade"] = torch.from_numpy(np.where(rs.uniform(size=(1, size, size)) < 0.1, 255,
+                                              synthetic._blocky(rs, 1, size, 4, 150)).astype(np.uint8))
+    u8["obj_detection"] = ids(5, 4, 0.3)
+    u8["ocr_detection"] = ids(3, 3, 0.5)
+    if case == 2:
+        u8["ocr_detection"][:] = 255
+    info = {"obj_detection": {str(i): int(rs.randint(0, 32)) for i in range(5)},
+            "ocr_detection": {i: {"features": torch.from_numpy(rs.standard_normal(64).astype(np.float32))} for i in range(3)}}
+    return u8, info
