@@ -84,9 +84,12 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def build_inputs(batch, seed, T=30):
+def build_inputs(batch, seed, T=30, compact=False):
     from prismer_b200 import synthetic
-    ex = synthetic.synth_experts(batch, 224, EXPERTS, 224, seed)
+    if compact:     # uint8 label maps + tables (prismer_b200/data.py) instead of the reference's fp32 stacks
+        ex = synthetic.synth_compact_experts(batch, 224, EXPERTS, 224, seed)
+    else:
+        ex = synthetic.synth_experts(batch, 224, EXPERTS, 224, seed)
     ids, mask = synthetic.synth_tokens(batch, T, 50265, seed)
     return ex, ids, mask
 
@@ -102,7 +105,8 @@ def nbytes(experts):
     n = 0
     for v in experts.values():
         for t in (v.values() if isinstance(v, dict) else [v]):
-            n += t.numel() * t.element_size()
+            for x in ((t.u8, t.table) if hasattr(t, "u8") else (t,)):
+                n += x.numel() * x.element_size()
     return n
 
 
@@ -128,7 +132,7 @@ def run_ours(args):
     if world > 1:
         dist.broadcast(st.master_t, 0); dist.broadcast(st.master_f, 0); st.refresh(force=True)
     opt = FusedAdamW(model, lr=5e-5, weight_decay=0.05, grad_scale=1.0 / world)
-    ex_h, ids_h, mask_h = build_inputs(B, 1000 + rank)
+    ex_h, ids_h, mask_h = build_inputs(B, 1000 + rank, compact=args.compact_inputs)
     ex_h = pin(ex_h); ids_h, mask_h = ids_h.pin_memory(), mask_h.pin_memory()
     ex_d = synthetic.experts_to(ex_h, dev); ids_d, mask_d = ids_h.to(dev), mask_h.to(dev)
     h2d = nbytes(ex_h) + ids_h.numel() * 8 + mask_h.numel() * 8
@@ -201,12 +205,7 @@ def run_ours(args):
     def prefetch():
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed)
-            for k, v in ex_h.items():
-                if isinstance(v, dict):
-                    for kk, vv in v.items():
-                        staging["ex"][k][kk].copy_(vv, non_blocking=True)
-                else:
-                    staging["ex"][k].copy_(v, non_blocking=True)
+            engine.copy_experts_(staging["ex"], ex_h, non_blocking=True)
             staging["ids"].copy_(ids_h, non_blocking=True); staging["mask"].copy_(mask_h, non_blocking=True)
             staging["labels"].copy_(labels_h, non_blocking=True)
             h2d_done.record(copy_stream)
@@ -219,7 +218,7 @@ def run_ours(args):
             consumed.record(main)
             prefetch()                                           # next batch's H2D overlaps this step's compute
             return step(None, None, None).item()
-        ex = {k: ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone()) for k, v in staging["ex"].items()}
+        ex = engine.clone_experts(staging["ex"])
         ids, mask = staging["ids"].clone(), staging["mask"].clone()
         consumed.record(main)
         prefetch()
@@ -290,7 +289,10 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "Prismer-BASE caption fine-tune step (fwd+bwd+1 grad all-reduce+AdamW), 224x224 + 6 expert maps, "
                                "T=30, freeze_vision, dropout 0.1", "per_gpu_batch": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "l2": "per-step inputs (1.28 GB/GPU) exceed the 126 MB L2"},
+                   "parallelism": f"dp{world}", "l2": ("activations written and re-read by one step (> 10 GB/GPU) exceed the 126 MB L2" if args.compact_inputs
+                                                       else "per-step inputs (1.28 GB/GPU) exceed the 126 MB L2"),
+                   "inputs": "compact: uint8 maps + tables expanded on the GPU (SURVEY 8f N1)" if args.compact_inputs
+                             else "reference format: fp32 [B,64,224,224] expert stacks (SURVEY a0)"},
         "e2e": {"value": round(world * B / (ms_e2e / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": h2d + labels_h.numel() * 8,
                 "d2h_bytes_per_step": 4, "note": "pinned H2D of batch i+1 overlaps step i (copy stream); loss.item() every step"},
         "gpu_launches": launches, "cuda_graph": graphed is not None,
@@ -462,6 +464,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph: launch every kernel of the step from Python")
+    ap.add_argument("--compact-inputs", action="store_true",
+                    help="feed uint8 label maps + tables (prismer_b200.data) instead of the reference's fp32 expert stacks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -452,9 +452,7 @@ def encoder_forward(vit, experts: Dict, save: bool, inst_table: Optional[torch.T
             pos_e, interp = _pos_for(vit, n_e, save)
             inst = table = None
             if e == "obj_detection":
-                inst = experts[e].get("instance")
-                if inst is None:                         # compact input: the label map IS the instance map (dataset/utils.py:146)
-                    inst = experts[e]["label"].u8.long()
+                inst = instance_map(experts[e])
                 table = inst_table if inst_table is not None else _instance_table(inst)
             ops.assemble_tokens(t, pos_e, xf[off * B:], D, B * D, B, n_e, D, gh, gw, inst, table,
                                 vit.instance_embedding._c16 if inst is not None else None)
@@ -1014,6 +1012,34 @@ def _canon_experts(experts):
     return {k: _canon_one(v, True) for k, v in experts.items()}
 
 
+def clone_experts(experts):
+    """Static input buffers for CUDA-graph capture (tensors, ``{'label','instance'}`` dicts and ``CompactMap`` values)."""
+    def one(v):
+        if isinstance(v, CompactMap):
+            return CompactMap(v.u8.clone(), v.table.clone())
+        return {kk: one(vv) for kk, vv in v.items()} if isinstance(v, dict) else v.clone()
+    return {k: one(v) for k, v in experts.items()}
+
+
+def copy_experts_(dst, src, non_blocking=True):
+    """Copy a new batch (host or device) into buffers made by ``clone_experts``; shapes must match the captured ones."""
+    for k, v in src.items():
+        d = dst[k]
+        if isinstance(v, CompactMap):
+            d.u8.copy_(v.u8, non_blocking=non_blocking)
+            d.table.copy_(v.table, non_blocking=non_blocking)
+        elif isinstance(v, dict):
+            copy_experts_(d, {kk: vv for kk, vv in v.items() if vv is not None and kk in d}, non_blocking)
+        else:
+            d.copy_(v, non_blocking=non_blocking)
+
+
+def instance_map(entry) -> torch.Tensor:
+    """int64 instance map of an ``obj_detection`` entry; for compact inputs the label map itself (dataset/utils.py:148)."""
+    inst = entry.get("instance")
+    return inst if inst is not None else entry["label"].u8.long()
+
+
 class GraphedTrainStep:
     """Forward + backward of one training step captured in ONE CUDA graph (static shapes): the ~1200 kernel launches of a
     step become a single ``cudaGraphLaunch``; dropout masks still change every replay (Philox key lives in device memory
@@ -1029,8 +1055,7 @@ class GraphedTrainStep:
         st = self.store = _store(model)
         st.refresh()
         dev = st.device
-        self.experts = {k: ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone())
-                        for k, v in _canon_experts(experts).items()}
+        self.experts = clone_experts(_canon_experts(experts))
         self.ids, self.mask, self.labels = input_ids.clone(), attention_mask.clone(), labels.clone()
         self.weights = weights.clone() if weights is not None else None
         self.has_inst = "obj_detection" in self.experts
@@ -1067,16 +1092,11 @@ class GraphedTrainStep:
 
     def _draw_table(self):
         if self.has_inst:
-            self.table.copy_(_instance_table(self.experts["obj_detection"]["instance"]), non_blocking=True)
+            self.table.copy_(_instance_table(instance_map(self.experts["obj_detection"])), non_blocking=True)
 
     def load_inputs(self, experts, input_ids, attention_mask, labels, weights=None, non_blocking=True):
         """Copy a new batch (host or device tensors) into the graph's static input buffers."""
-        for k, v in experts.items():
-            if isinstance(v, dict):
-                for kk, vv in v.items():
-                    self.experts[k][kk].copy_(vv, non_blocking=non_blocking)
-            else:
-                self.experts[k].copy_(v, non_blocking=non_blocking)
+        copy_experts_(self.experts, experts, non_blocking)
         self.ids.copy_(input_ids, non_blocking=non_blocking)
         self.mask.copy_(attention_mask, non_blocking=non_blocking)
         self.labels.copy_(labels, non_blocking=non_blocking)

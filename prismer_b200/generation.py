@@ -75,8 +75,7 @@ class GraphedCaptioner:
         st = self.store = engine._store(model)
         st.refresh()
         dev = st.device
-        self.experts = {k: ({kk: vv.clone() for kk, vv in v.items()} if isinstance(v, dict) else v.clone())
-                        for k, v in engine._canon_experts(experts).items()}
+        self.experts = engine.clone_experts(engine._canon_experts(experts))
         self.T0, self.max_length, self.min_length = prefix_ids.shape[1], max_length, min_length
         self.prefix = prefix_ids.clone()
         self.ids = torch.full((prefix_ids.shape[0], max_length), dec.config.pad_token_id, dtype=torch.int64, device=dev)
@@ -103,15 +102,10 @@ class GraphedCaptioner:
 
     def _draw_table(self):
         if self.has_inst:
-            self.table.copy_(engine._instance_table(self.experts["obj_detection"]["instance"]), non_blocking=True)
+            self.table.copy_(engine._instance_table(engine.instance_map(self.experts["obj_detection"])), non_blocking=True)
 
     def load_inputs(self, experts, non_blocking=True):
-        for k, v in experts.items():
-            if isinstance(v, dict):
-                for kk, vv in v.items():
-                    self.experts[k][kk].copy_(vv, non_blocking=non_blocking)
-            else:
-                self.experts[k].copy_(v, non_blocking=non_blocking)
+        engine.copy_experts_(self.experts, experts, non_blocking)
 
     def __call__(self) -> torch.Tensor:
         """Replay on the current static inputs; returns the [B, max_length] id buffer (use ``trim_finished`` for HF's length)."""
