@@ -12,6 +12,99 @@ import torch.distributed as dist
 from . import engine
 
 
+# ------------------------------------------------------------------------------------------------ data-loader side of prepare()
+def _to_device(obj, device, non_blocking=True):
+    """What accelerate's prepared loaders do with ``device_placement=True``: tensors (and anything with a tensor-like ``.to``, e.g.
+    ``data.CompactMap``) inside nested dict / list / tuple batches go to the device; strings and numbers are left alone."""
+    if torch.is_tensor(obj) or (hasattr(obj, "to") and hasattr(obj, "u8")):
+        return obj.to(device, non_blocking=non_blocking)
+    if isinstance(obj, dict):
+        return type(obj)((k, _to_device(v, device, non_blocking)) for k, v in obj.items())
+    if isinstance(obj, (list, tuple)) and not isinstance(obj, str):
+        return type(obj)(_to_device(v, device, non_blocking) for v in obj)
+    return obj
+
+
+class BatchShard:
+    """accelerate's ``BatchSamplerShard`` (split_batches=False, even_batches=True): of every ``world`` consecutive batches of the
+    base batch sampler, process ``rank`` takes the ``rank``-th.  A short last batch / an incomplete last round is completed with
+    indices from the start of the epoch so that every process runs the same number of equally sized steps (the duplicated
+    samples are dropped again by ``Accelerator.gather_for_metrics``)."""
+
+    def __init__(self, batch_sampler, world: int, rank: int):
+        self.batch_sampler, self.world, self.rank = batch_sampler, world, rank
+        self.batch_size = getattr(batch_sampler, "batch_size", None)
+        self.drop_last = getattr(batch_sampler, "drop_last", False)
+
+    def __len__(self):
+        n = len(self.batch_sampler)
+        return n // self.world if self.drop_last else -(-n // self.world)
+
+    def __iter__(self):
+        first, group = [], []
+        for batch in self.batch_sampler:
+            batch = list(batch)
+            if len(first) < (self.batch_size or len(batch)) * self.world:
+                first += batch                                   # indices to recycle when the epoch does not divide evenly
+            group.append(batch)
+            if len(group) == self.world and len(batch) == (self.batch_size or len(batch)):
+                yield group[self.rank]
+                group = []
+        if group and not self.drop_last:
+            bs = self.batch_size or len(group[0])
+            flat = [i for b in group for i in b]
+            need = bs * self.world - len(flat)
+            pool = first
+            while need > 0 and pool:
+                take = pool[:need]
+                flat += take
+                need -= len(take)
+            yield flat[self.rank * bs:(self.rank + 1) * bs]
+
+
+class ShardedLoader:
+    """Prepared data loader: this process' shard of the batches, already on the device.  Keeps ``.dataset`` / ``len()`` (the
+    reference reads ``test_loader.dataset.data_list`` and ``len(train_loader)``, train_caption.py:127,150)."""
+
+    def __init__(self, loader, accelerator):
+        from torch.utils.data import DataLoader
+        self.base, self.acc = loader, accelerator
+        self.dataset = loader.dataset
+        self.batch_size = loader.batch_size
+        world, rank = accelerator.num_processes, accelerator.process_index
+        if world > 1:
+            shard = BatchShard(loader.batch_sampler, world, rank)
+            kw = dict(num_workers=loader.num_workers, collate_fn=loader.collate_fn, pin_memory=loader.pin_memory,
+                      timeout=loader.timeout, worker_init_fn=loader.worker_init_fn)
+            if loader.num_workers > 0:
+                kw.update(prefetch_factor=loader.prefetch_factor, persistent_workers=loader.persistent_workers)
+            self.loader = DataLoader(loader.dataset, batch_sampler=shard, **kw)
+        else:
+            self.loader = loader
+        total, per_round = len(loader.dataset), (loader.batch_size or 1) * world
+        self.remainder = total % per_round if not getattr(loader, "drop_last", False) else 0
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        self.acc._end_of_loader, self.acc._remainder = False, 0
+        it = iter(self.loader)
+        try:
+            cur = next(it)
+        except StopIteration:
+            return
+        while True:
+            try:
+                nxt = next(it)
+            except StopIteration:
+                self.acc._end_of_loader, self.acc._remainder = True, self.remainder
+                yield _to_device(cur, self.acc.device)
+                return
+            yield _to_device(cur, self.acc.device)
+            cur = nxt
+
+
 class Accelerator:
     def __init__(self, mixed_precision: str = "bf16", **_):
         self.mixed_precision = mixed_precision
@@ -29,6 +122,7 @@ class Accelerator:
             self.device = torch.device("cpu")
         self._models = []
         self._fused_optimizer = False
+        self._end_of_loader, self._remainder = False, 0
 
     @property
     def is_main_process(self):
@@ -52,6 +146,8 @@ class Accelerator:
             elif hasattr(o, "grad_scale"):
                 o.grad_scale = 1.0 / self.num_processes
                 self._fused_optimizer = True
+            elif isinstance(o, torch.utils.data.DataLoader):
+                o = ShardedLoader(o, self)         # this rank's batches, moved to the device (train_caption.py:115-117,126)
             out.append(o)
         return out[0] if len(out) == 1 else tuple(out)
 
@@ -66,12 +162,33 @@ class Accelerator:
         if self.use_distributed:
             dist.barrier()
 
-    def gather_for_metrics(self, t):
+    def gather(self, obj):
+        """Concatenate every process' tensors along dim 0 in rank order (nested tuple / list / dict of tensors)."""
         if not self.use_distributed:
-            return t
-        out = [torch.empty_like(t) for _ in range(self.num_processes)]
-        dist.all_gather(out, t.contiguous())
-        return torch.cat(out, 0)
+            return obj
+        if torch.is_tensor(obj):
+            t = obj.contiguous()
+            if t.dim() == 0:
+                t = t[None]
+            out = [torch.empty_like(t) for _ in range(self.num_processes)]
+            dist.all_gather(out, t)
+            return torch.cat(out, 0)
+        if isinstance(obj, dict):
+            return type(obj)((k, self.gather(v)) for k, v in obj.items())
+        if isinstance(obj, (list, tuple)) and all(torch.is_tensor(v) or isinstance(v, (list, tuple, dict)) for v in obj):
+            return type(obj)(self.gather(v) for v in obj)
+        raise TypeError(f"gather: unsupported object of type {type(obj).__name__} (tensors in tuples / lists / dicts only)")
+
+    def gather_for_metrics(self, obj):
+        """``gather`` + drop the samples that were duplicated to even out the last round of a prepared loader
+        (train_caption.py:147,190: ``data_ids, captions = accelerator.gather_for_metrics((data_ids, captions))``)."""
+        out = self.gather(obj)
+        if self.use_distributed and self._end_of_loader and self._remainder > 0:
+            n = self._remainder
+            cut = lambda o: (o[:n] if torch.is_tensor(o) else (type(o)((k, cut(v)) for k, v in o.items()) if isinstance(o, dict)
+                                                                else type(o)(cut(v) for v in o)))
+            out = cut(out)
+        return out
 
     def save(self, obj, path):
         if self.is_main_process:
