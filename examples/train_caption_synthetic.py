@@ -34,6 +34,7 @@ def main():
     ap.add_argument('--batch', type=int, default=8)
     ap.add_argument('--seed', type=int, default=42)
     ap.add_argument('--torch_adamw', action='store_true')
+    ap.add_argument('--compact', action='store_true', help="uint8 label maps + tables through the loader (prismer_b200.data)")
     args = ap.parse_args()
     config = {'experts': synthetic.DEFAULT_EXPERTS, 'image_resolution': 224, 'prismer_model': 'prismer_base', 'freeze': 'freeze_vision',
               'batch_size_train': args.batch, 'init_lr': 5e-5, 'weight_decay': 0.05, 'min_lr': 0, 'max_epoch': 1,
@@ -51,13 +52,15 @@ def main():
         model = accelerator.prepare(model)
         optimizer = accelerator.prepare(FusedAdamW(model, lr=config['init_lr'], weight_decay=config['weight_decay']))
 
-    words = "a an the dog cat man woman street table plate bus train sitting standing holding red blue green two three".split()
-    rng = random.Random(args.seed + accelerator.process_index)
-    experts = synthetic.experts_to(synthetic.synth_experts(args.batch, 224, config['experts'], 224, accelerator.process_index), accelerator.device)
+    # reference: train_dataset, test_dataset = create_dataset('caption', config); train_loader = create_loader(...)  (train_caption.py:49-52)
+    dataset = synthetic.SyntheticCaptionDataset(args.steps * args.batch * accelerator.num_processes, config['experts'],
+                                                config['image_resolution'], compact=args.compact, prefix=config['prefix'], seed=args.seed)
+    train_loader = torch.utils.data.DataLoader(dataset, batch_size=config['batch_size_train'], num_workers=4, pin_memory=True,
+                                               collate_fn=dataset.collate, shuffle=True, drop_last=True)
+    train_loader = accelerator.prepare(train_loader)                 # this rank's batches, already on the device (train_caption.py:115)
     model.train()
-    for i in range(args.steps):
-        caption = [config['prefix'] + ' ' + ' '.join(rng.choice(words) for _ in range(rng.randint(4, 10))) for _ in range(args.batch)]
-        cosine_lr_schedule(optimizer, i, args.steps, config['init_lr'], config['min_lr'])
+    for i, (experts, caption) in enumerate(train_loader):
+        cosine_lr_schedule(optimizer, i, len(train_loader), config['init_lr'], config['min_lr'])
 
         loss = model(experts, caption, prefix=config['prefix'])
 

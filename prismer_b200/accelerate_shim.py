@@ -81,6 +81,14 @@ class ShardedLoader:
             self.loader = DataLoader(loader.dataset, batch_sampler=shard, **kw)
         else:
             self.loader = loader
+        # shuffling must draw the SAME permutation on every rank (accelerate synchronises the sampler's generator): one seed from
+        # rank 0, advanced per epoch
+        self.epoch = 0
+        seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64)
+        if world > 1:
+            seed = seed.to(accelerator.device) if dist.get_backend() == "nccl" else seed
+            dist.broadcast(seed, 0)
+        self.seed = int(seed)
         total, per_round = len(loader.dataset), (loader.batch_size or 1) * world
         self.remainder = total % per_round if not getattr(loader, "drop_last", False) else 0
 
@@ -89,6 +97,10 @@ class ShardedLoader:
 
     def __iter__(self):
         self.acc._end_of_loader, self.acc._remainder = False, 0
+        sampler = getattr(self.base, "sampler", None)
+        if isinstance(sampler, torch.utils.data.RandomSampler) and self.acc.num_processes > 1:
+            sampler.generator = torch.Generator().manual_seed(self.seed + self.epoch)
+        self.epoch += 1
         it = iter(self.loader)
         try:
             cur = next(it)

@@ -192,3 +192,39 @@ def expand_compact_on_host(experts: Dict) -> Dict:
         else:
             out[k] = v
     return out
+
+
+class SyntheticCaptionDataset(torch.utils.data.Dataset):
+    """Stands in for ``dataset/caption_dataset.py:Caption`` (train split): ``__getitem__ -> (experts, caption)`` with per-sample
+    tensors in the reference's format, or -- ``compact=True`` -- uint8 maps pushed through ``data.compact_label_process`` the way a
+    patched ``Caption.__getitem__`` would.  Use ``collate`` as the loader's ``collate_fn``."""
+
+    WORDS = "a an the dog cat man woman street table plate bus train sitting standing holding red blue green two three".split()
+
+    def __init__(self, n: int, experts: Iterable[str] = DEFAULT_EXPERTS, image_resolution: int = 224, label_size: int = 224,
+                 compact: bool = False, prefix: str = "A picture of", seed: int = 0):
+        self.n, self.experts, self.res, self.label, self.compact, self.prefix, self.seed = (n, list(experts), image_resolution,
+                                                                                           label_size, compact, prefix, seed)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        if self.compact:
+            batch = synth_compact_experts(1, self.res, self.experts, self.label, self.seed * 100003 + i)
+        else:
+            batch = synth_experts(1, self.res, self.experts, self.label, self.seed * 100003 + i)
+        def first(v):
+            if isinstance(v, dict):
+                return {k: first(x) for k, x in v.items()}
+            if hasattr(v, "u8"):
+                return type(v)(v.u8[0], v.table[0] if v.table.dim() == 3 else v.table)
+            return v[0]
+        rs = _rs(self.seed, f"caption.{i}")
+        caption = self.prefix + " " + " ".join(self.WORDS[j] for j in rs.randint(0, len(self.WORDS), rs.randint(4, 11)))
+        return {k: first(v) for k, v in batch.items()}, caption
+
+    @staticmethod
+    def collate(samples):
+        from . import data
+        return data.collate_experts([s[0] for s in samples]), [s[1] for s in samples]

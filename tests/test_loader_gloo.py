@@ -26,11 +26,12 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, n, bs, out):
+def _worker(rank, world, port, n, bs, out, shuffle=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     from prismer_b200.accelerate_shim import Accelerator
     acc = Accelerator()
-    loader = acc.prepare(DataLoader(_Toy(n), batch_size=bs, shuffle=False))
+    torch.manual_seed(100 + rank)                                   # ranks have DIFFERENT global RNG states
+    loader = acc.prepare(DataLoader(_Toy(n), batch_size=bs, shuffle=shuffle))
     assert loader.dataset.n == n
     seen, gathered, steps = [], [], 0
     for experts, ids in loader:
@@ -46,11 +47,17 @@ def _worker(rank, world, port, n, bs, out):
     dist.destroy_process_group()
 
 
-def _run(n, bs, world=2):
+def _run(n, bs, world=2, shuffle=False):
     port = _free_port()
     out = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, n, bs, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n, bs, out, shuffle), nprocs=world, join=True)
     return out
+
+
+def test_shuffled_epoch_uses_one_permutation_on_all_ranks():
+    out = _run(n=16, bs=4, shuffle=True)
+    assert sorted(out[0][0] + out[1][0]) == list(range(16))          # disjoint shards covering the epoch
+    assert out[0][1] == out[1][1] and sorted(out[0][1]) == list(range(16)) and out[0][1] != list(range(16))
 
 
 def test_even_epoch_is_partitioned_in_interleaved_batch_order():
