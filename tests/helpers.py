@@ -1,6 +1,5 @@
 """Shared helpers for the test-suite (test infrastructure; may import ``oracle``)."""
 import os
-import random
 
 import numpy as np
 import torch

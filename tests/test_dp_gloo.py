@@ -17,7 +17,7 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from types import SimpleNamespace
-    from prismer_b200 import accelerate_shim, engine
+    from prismer_b200 import accelerate_shim
     torch.manual_seed(0)
     w = torch.randn(16, 8)
     x = torch.randn(4 * world, 8)[rank * 4:(rank + 1) * 4]          # this rank's shard of the global batch

@@ -14,7 +14,7 @@ import pytest
 import torch
 
 from prismer_b200 import data, synthetic
-from tests.helpers import GOLD, TINY_DEC, build_model, label_case
+from tests.helpers import GOLD, build_model, label_case
 
 # Written after this round's GPU budget was spent: the first hardware run is the driver's round-end run.  Non-strict xfail so a
 # defect HERE shows up as "x" without masking the hardware-validated suite that runs before it ("X" = passed); the marker is
