@@ -215,7 +215,8 @@ int prismer_label_resample(const void* labels, const float* table, long long tab
  * EXPERIMENTAL (round-2 candidate; compiled and exported but not on the default path and not yet validated on hardware):
  * attention as batched tcgen05 GEMMs over (batch, head) problems with L2-resident score matrices.
  *   C_i[M,N] = epilogue(alpha * op(A_i) . op(B_i)^T),  X_i = X + bo * X_bs_outer + bi * X_bs_inner (elements)
- *   mode 0: C = alpha*acc;   mode 1 (softmax backward): C = aux * (acc - rowvec[i*rowvec_bs + row]) * alpha
+ *   mode 0: C = alpha*acc;   mode 1 (softmax backward): C = aux * (acc - rowvec[i*rowvec_bs + row]) * alpha;
+ *   mode 2 (probabilities from the forward's saved log-sum-exp): C = exp(alpha*acc - rowvec[i*rowvec_bs + row])
  * Replaces (when enabled) the score / value products of nn.MultiheadAttention (vit.py:52-53) and their backward.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct PrismerBatchedGemmArgs {

@@ -1,6 +1,7 @@
 // EXPERIMENTAL (round-2 candidate, compiled but NOT on the default path and not yet validated on hardware):
 // batched variant of the persistent tcgen05 GEMM of gemm_sm100.cu for attention expressed as matrix products over
-// (batch, head) problems -- S = scale*Q.K^T, O = P.V, dV = P^T.dO, dS = P*(dO.V^T - delta)*scale, dQ = dS.K, dK = dS^T.Q -- with the
+// (batch, head) problems -- S = scale*Q.K^T (or P = exp(scale*Q.K^T - lse) straight from the epilogue), O = P.V, dV = P^T.dO,
+// dS = P*(dO.V^T - delta)*scale, dQ = dS.K, dK = dS^T.Q -- with the
 // score / probability matrices of the ViT shape (384 x 260 x 260 bf16 = 52 MB per layer) staying L2-resident.
 //
 //   C_i[M,N] = epilogue(alpha * op(A_i) . op(B_i)^T),  i = (bo, bi) in [0, batch_outer) x [0, batch_inner)
@@ -39,6 +40,7 @@ struct BatchedEpi {
   const bf16* aux; long long ldaux, aux_bo, aux_bi;   // mode 1: probabilities P (same logical layout as C)
   const float* rowvec; long long rowvec_bs;            // mode 1: delta, fp32 [batch, M]
   int mode;                                            // 0: C = alpha*acc     1: C = aux * (acc - rowvec[row]) * alpha
+                                                       // 2: C = exp(alpha*acc - rowvec[row])  (probabilities from saved LSE)
   float alpha;
   int batch_inner;
 };
@@ -174,7 +176,7 @@ gemm_bf16_batched_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const bool row_ok = row < M;
       const int rows_valid = min(32, M - (m0 + q * 32));
       float rv = 0.f;
-      if (ep.mode == 1 && row_ok) rv = ep.rowvec[static_cast<long long>(prob) * ep.rowvec_bs + row];
+      if (ep.mode != 0 && row_ok) rv = ep.rowvec[static_cast<long long>(prob) * ep.rowvec_bs + row];
 #pragma unroll 1
       for (int c = chalf * 32; c < BN; c += 64) {
         uint32_t raw[32];
@@ -199,6 +201,9 @@ gemm_bf16_batched_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             } else {
               _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < N) { v[j] = __bfloat162float(ap[j]) * (v[j] - rv) * ep.alpha; }
             }
+          } else if (ep.mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __expf(v[j] * ep.alpha - rv);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= ep.alpha;
@@ -286,6 +291,8 @@ extern "C" int prismer_gemm_bf16_batched(const PrismerBatchedGemmArgs* a, cudaSt
   if (!a || a->M <= 0 || a->N <= 0 || a->K <= 0 || a->batch_outer <= 0 || a->batch_inner <= 0) return PRISMER_ERR_SHAPE;
   if ((a->lda % 8) || (a->ldb % 8) || (a->ldc % 8)) return PRISMER_ERR_ALIGN;
   if (a->mode == 1 && (!a->aux || !a->rowvec || (a->ldaux % 8))) return PRISMER_ERR_SHAPE;
+  if (a->mode == 2 && !a->rowvec) return PRISMER_ERR_SHAPE;
+  if (a->mode < 0 || a->mode > 2) return PRISMER_ERR_SHAPE;
   const int bn = a->N <= 64 ? 64 : (a->N <= 128 ? 128 : 256);
   CUtensorMap ta, tb;
   int rc;

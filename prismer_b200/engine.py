@@ -538,6 +538,10 @@ def _pos_grad(vit, dtok_sf, B, n_tok, D, n_slots, slot_stride, interp):
 import os as _os
 
 ATTN_UNFUSED = _os.environ.get("PRISMER_ATTN_UNFUSED") == "1"
+# "bwd": keep the fused flash forward (nothing but the LSE saved) and run only the BACKWARD as batched GEMMs, recomputing the
+# probabilities from the LSE in the epilogue of the score GEMM -- the backward is where the mma.sync kernels lose most
+# (390 us per ViT layer against ~90 us estimated), and no [B*H, S, S] tensor outlives the layer's backward.
+ATTN_UNFUSED_BWD = _os.environ.get("PRISMER_ATTN_UNFUSED") == "bwd"
 
 
 def _unfused_attn_fwd(qkv, o, B, S, H, save):
@@ -558,10 +562,17 @@ def _unfused_attn_fwd(qkv, o, B, S, H, save):
 
 
 def _unfused_attn_bwd(do, qkv, o, P, dqkv, B, S, H):
+    """``P``: the probabilities saved by ``_unfused_attn_fwd`` ([B*H, S, Sp] bf16), or the fused forward's LSE ([B, H, S] fp32),
+    from which they are recomputed: P = exp(scale * Q K^T - lse) in the score GEMM's epilogue."""
     D = o.shape[1]
     d = D // H
-    Sp = P.shape[2]
     ld = B * 3 * D
+    if P.dtype == F32:
+        lse, Sp = P, (S + 7) // 8 * 8
+        P = torch.empty((B * H, S, Sp), dtype=BF16, device=qkv.device)
+        ops.gemm_batched(qkv, qkv[:, D:], P, S, S, d, lda=ld, ldb=ld, ldc=Sp, batch_outer=B, batch_inner=H, a_bs=(3 * D, d),
+                         b_bs=(3 * D, d), c_bs=(H * S * Sp, S * Sp), rowvec=lse, rowvec_bs=S, mode=2, alpha=d ** -0.5)
+    Sp = P.shape[2]
     qs, ps, os_ = (3 * D, d), (H * S * Sp, S * Sp), (D, d)
     delta = ops.attn_delta(do, o, B, H, S, d)
     # dV = P^T dO
@@ -610,8 +621,8 @@ def _vit_block_bwd(blk, adp, dx3, sv, B, S):
     _lin_grads(dx1, sv.o, at.out_proj)
     dqkv = torch.empty_like(sv.qkv)
     q3, d3 = _sf(sv.qkv, S, B), _sf(dqkv, S, B)
-    if sv.lse is not None and sv.lse.dim() == 3 and sv.lse.dtype == BF16:      # experimental unfused path saved P
-        _unfused_attn_bwd(do, sv.qkv, sv.o, sv.lse, dqkv, B, S, H)
+    if sv.lse is not None and sv.lse.dim() == 3 and (sv.lse.dtype == BF16 or (ATTN_UNFUSED_BWD and D // H == 64)):
+        _unfused_attn_bwd(do, sv.qkv, sv.o, sv.lse, dqkv, B, S, H)             # experimental: saved P, or LSE -> recomputed P
     else:
         ops.attention_bwd(_sf(do, S, B), q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], _sf(sv.o, S, B), sv.lse, H,
                           dq=d3[..., :D], dk=d3[..., D:2 * D], dv=d3[..., 2 * D:])
