@@ -230,6 +230,7 @@ typedef struct PrismerBatchedGemmArgs {
   const float* rowvec; long long rowvec_bs;
   int mode;
   float alpha;
+  int force_bn;   /* 0 = pick the N tile (64 / 128 / 256) that pads N least; tuning override otherwise */
 } PrismerBatchedGemmArgs;
 int prismer_gemm_bf16_batched(const PrismerBatchedGemmArgs* args, cudaStream_t stream);
 /* in place row softmax of bf16 scores [rows, ld] over the first Lk columns (padding columns are zeroed). */

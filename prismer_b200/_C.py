@@ -42,7 +42,7 @@ class BatchedGemmArgs(Structure):
         ("a_bs_outer", c_longlong), ("a_bs_inner", c_longlong), ("b_bs_outer", c_longlong), ("b_bs_inner", c_longlong),
         ("c_bs_outer", c_longlong), ("c_bs_inner", c_longlong),
         ("aux", c_void_p), ("ldaux", c_longlong), ("aux_bs_outer", c_longlong), ("aux_bs_inner", c_longlong),
-        ("rowvec", c_void_p), ("rowvec_bs", c_longlong), ("mode", c_int), ("alpha", c_float),
+        ("rowvec", c_void_p), ("rowvec_bs", c_longlong), ("mode", c_int), ("alpha", c_float), ("force_bn", c_int),
     ]
 
 

@@ -293,7 +293,16 @@ extern "C" int prismer_gemm_bf16_batched(const PrismerBatchedGemmArgs* a, cudaSt
   if (a->mode == 1 && (!a->aux || !a->rowvec || (a->ldaux % 8))) return PRISMER_ERR_SHAPE;
   if (a->mode == 2 && !a->rowvec) return PRISMER_ERR_SHAPE;
   if (a->mode < 0 || a->mode > 2) return PRISMER_ERR_SHAPE;
-  const int bn = a->N <= 64 ? 64 : (a->N <= 128 ? 128 : 256);
+  // N tile: least padded columns (attention scores, N = 260: 5 x 64 = 320 instead of 2 x 256 = 512); ties -> the larger tile
+  int bn = 256;
+  {
+    long long best = -1;
+    for (int cand : {256, 128, 64}) {
+      const long long padded = static_cast<long long>((a->N + cand - 1) / cand) * cand;
+      if (best < 0 || padded < best) { best = padded; bn = cand; }
+    }
+  }
+  if (a->force_bn == 64 || a->force_bn == 128 || a->force_bn == 256) bn = a->force_bn;
   CUtensorMap ta, tb;
   int rc;
   if (!a->transA) rc = make_map_4d(&ta, a->A, a->K, a->M, a->lda, a->batch_inner, a->a_bs_inner, a->batch_outer, a->a_bs_outer, BK, BM);

@@ -421,7 +421,7 @@ def unpad_add(src2d, dst2d):
 
 # ------------------------------------------------------------------------------------------------ EXPERIMENTAL (round-2 candidate)
 def gemm_batched(a_ptr_view, b_ptr_view, c_view, M, N, K, *, lda, ldb, ldc, trans_a=False, trans_b=False, batch_outer=1, batch_inner=1,
-                 a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), aux=None, ldaux=0, aux_bs=(0, 0), rowvec=None, rowvec_bs=0, mode=0, alpha=1.0):
+                 a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), aux=None, ldaux=0, aux_bs=(0, 0), rowvec=None, rowvec_bs=0, mode=0, alpha=1.0, force_bn=0):
     """Batched tcgen05 GEMM over (batch_outer x batch_inner) problems; every tensor argument is a torch tensor whose
     ``data_ptr()`` is problem (0, 0); ``*_bs = (outer stride, inner stride)`` in elements.  See include/prismer_sm100.h."""
     a = _C.BatchedGemmArgs()
@@ -438,7 +438,7 @@ def gemm_batched(a_ptr_view, b_ptr_view, c_view, M, N, K, *, lda, ldb, ldc, tran
         a.aux_bs_outer, a.aux_bs_inner = aux_bs
     if rowvec is not None:
         a.rowvec, a.rowvec_bs = rowvec.data_ptr(), rowvec_bs
-    a.mode, a.alpha = mode, alpha
+    a.mode, a.alpha, a.force_bn = mode, alpha, force_bn
     check(_C.lib().prismer_gemm_bf16_batched(ctypes.byref(a), _stream()), "gemm_bf16_batched")
 
 
