@@ -1,0 +1,102 @@
+"""-m gpu: size-independent properties of the hot path at the full Prismer-BASE dimensions (BASELINE.json configs 2/3: ViT-B/16 +
+6 experts + roberta-base, 224 px, T = 30) where an fp32 CPU oracle run would take minutes per sample:
+
+  * batch-permutation equivariance of the eval forward (samples are independent: per-row GEMM / LayerNorm / attention
+    arithmetic does not depend on the batch position);
+  * padding invariance of the caption loss (extra <pad> columns with mask 0 / label -100 change nothing);
+  * batch additivity of the gradient: grad(A u B) = (|A| grad(A) + |B| grad(B)) / |A u B| (loss is a batch mean; eval-mode
+    BatchNorm and no dropout make samples independent) -- exercises every wgrad reduction of the backward at full size;
+  * greedy decoding is prefix-consistent: generate(max_length=12) is the first 12 tokens of generate(max_length=20)."""
+import random
+
+import pytest
+import torch
+
+from prismer_b200 import synthetic
+
+# Written after this round's GPU budget was spent: the first hardware run is the driver's round-end run.  Non-strict xfail so a
+# defect HERE shows up as "x" without masking the hardware-validated suite that runs before it ("X" = passed).
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending")]
+EXPERTS = synthetic.DEFAULT_EXPERTS
+B, T = 8, 30
+
+
+@pytest.fixture(scope="module")
+def base():
+    from prismer_b200.prismer_caption import PrismerCaption
+    torch.manual_seed(2)
+    m = PrismerCaption({"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": 224, "freeze": "freeze_vision"})
+    m.cuda().eval()
+    ex = synthetic.experts_to(synthetic.synth_experts(B, 224, EXPERTS, 224, 21), "cuda")
+    ids, mask = synthetic.synth_tokens(B, T, 50265, 21, ragged=True)
+    return m, ex, ids.cuda(), mask.cuda()
+
+
+def _take(ex, idx):
+    return {k: ({kk: vv[idx] for kk, vv in v.items()} if isinstance(v, dict) else v[idx]) for k, v in ex.items()}
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def test_eval_forward_is_batch_permutation_equivariant(base):
+    m, ex, ids, mask = base
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).cuda()
+    with torch.no_grad():
+        random.seed(7); enc = m.expert_encoder(ex)                                  # [S, B, D]
+        random.seed(7); enc_p = m.expert_encoder(_take(ex, perm))
+        lo = m.text_decoder(ids, attention_mask=mask, encoder_hidden_states=enc.transpose(0, 1)).logits
+        lo_p = m.text_decoder(ids[perm], attention_mask=mask[perm], encoder_hidden_states=enc_p.transpose(0, 1)).logits
+    torch.cuda.synchronize()
+    e1, e2 = _rel(enc_p.float(), enc[:, perm].float()), _rel(lo_p, lo[perm])
+    print(f"permutation equivariance: encoder rel {e1:.1e} (bit-identical {bool(torch.equal(enc_p, enc[:, perm]))}), logits rel {e2:.1e}")
+    assert e1 < 1e-6 and e2 < 1e-6
+
+
+def test_caption_loss_is_padding_invariant(base):
+    from prismer_b200 import engine
+    m, ex, ids, mask = base
+    labels = ids.masked_fill(ids == 1, -100); labels[:, :4] = -100
+    pad = 8
+    ids2 = torch.cat([ids, torch.ones(B, pad, dtype=ids.dtype, device=ids.device)], 1)
+    mask2 = torch.cat([mask, torch.zeros(B, pad, dtype=mask.dtype, device=mask.device)], 1)
+    labels2 = torch.cat([labels, torch.full((B, pad), -100, dtype=labels.dtype, device=labels.device)], 1)
+    with torch.no_grad():
+        random.seed(9); l1 = float(engine.train_loss(m, ex, ids, mask, labels))
+        random.seed(9); l2 = float(engine.train_loss(m, ex, ids2, mask2, labels2))
+    print(f"padding invariance: loss {l1:.6f} vs {l2:.6f}")
+    assert abs(l1 - l2) < 1e-3 * abs(l1)
+
+
+def test_gradient_is_additive_over_the_batch(base):
+    from prismer_b200 import engine
+    m, ex, ids, mask = base
+    labels = ids.masked_fill(ids == 1, -100); labels[:, :4] = -100
+    st = engine._store(m)
+
+    def grad(idx):
+        random.seed(11)                                   # same instance-embedding draw for every sub-batch (ids 0..4 present in all)
+        loss = engine.train_loss(m, _take(ex, idx), ids[idx], mask[idx], labels[idx])
+        loss.backward()
+        torch.cuda.synchronize()
+        return st.grad_t.clone(), float(loss)
+
+    full, lf = grad(torch.arange(B, device="cuda"))
+    a, la = grad(torch.arange(0, B // 2, device="cuda"))
+    b, lb = grad(torch.arange(B // 2, B, device="cuda"))
+    comb = 0.5 * (a + b)
+    err = _rel(comb, full)
+    print(f"batch additivity: loss {lf:.5f} vs {(la + lb) / 2:.5f}; flat gradient rel-L2 {err:.2e} (|g| {float(full.norm()):.3e})")
+    assert abs(lf - (la + lb) / 2) < 1e-3 * abs(lf)
+    assert err < 3e-2                                     # bf16 dgrad / activation rounding differs between the two tilings
+
+
+def test_greedy_is_prefix_consistent(base):
+    m, ex, _, _ = base
+    prefix = torch.tensor([[0, 250, 2170, 9]], device="cuda").repeat(B, 1)
+    with torch.no_grad():
+        random.seed(13); enc = m.expert_encoder(ex).transpose(0, 1)
+        short = m.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=12, min_length=12)
+        long = m.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=20, min_length=12)
+    assert short.shape[1] == 12 and torch.equal(short, long[:, :12])
