@@ -16,6 +16,8 @@ OBJ_DIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
+if os.environ.get("PRISMER_PDL") == "1":      # opt-in experiment: programmatic dependent launch for the hot kernels (common.cuh)
+    NVCC_FLAGS.append("-DPRISMER_PDL")
 
 
 def _nvcc() -> str:

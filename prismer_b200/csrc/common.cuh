@@ -168,5 +168,33 @@ __device__ __forceinline__ bf16x8 pack8(const float* f) {
   return make_uint4(pack_bf162(f[0], f[1]), pack_bf162(f[2], f[3]), pack_bf162(f[4], f[5]), pack_bf162(f[6], f[7]));
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (opt-in build flag)
+// -DPRISMER_PDL (PRISMER_PDL=1 python -m prismer_b200.build): the hot kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and start with griddepcontrol.launch_dependents + griddepcontrol.wait, so
+// the next kernel's launch / prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps the previous kernel's tail;
+// every global read or write of such a kernel comes after the wait.  Without the flag (the default, the hardware-validated
+// build) both macros are empty and pdl_launch is a plain <<<>>> launch.  Round-2 experiment; see NOTES_NEXT_ROUND.md.
+#ifdef PRISMER_PDL
+#define PDL_GRID_SYNC() do { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+#else
+#define PDL_GRID_SYNC() ((void)0)
+#endif
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline void pdl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+#ifdef PRISMER_PDL
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+#else
+  kern<<<grid, block, smem, stream>>>(static_cast<KArgs>(args)...);
+#endif
+}
+#endif
+
 static inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? PRISMER_OK : PRISMER_ERR_CUDA; }
 #define LAUNCH_CHECK() cuda_status(cudaGetLastError())

@@ -9,6 +9,7 @@ namespace {
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ out,
                                                      int M, int N, int rows_per_block) {
   __shared__ float red[8][256];
+  PDL_GRID_SYNC();
   const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col0 = blockIdx.x * 256 + cv * 8;
   const int r0 = blockIdx.y * rows_per_block;
@@ -290,7 +291,7 @@ extern "C" int prismer_colsum(const void* x, long long ldx, float* out, int M, i
   int rpb = (M + gy - 1) / gy;
   rpb = ((rpb + 7) / 8) * 8;
   gy = (M + rpb - 1) / rpb;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, out, M, N, rpb);
+  pdl_launch(colsum_kernel, dim3(gx, gy), dim3(256), 0, stream, reinterpret_cast<const bf16*>(x), ldx, out, M, N, rpb);
   return LAUNCH_CHECK();
 }
 

@@ -81,6 +81,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PDL_GRID_SYNC();   // (opt-in build) everything above overlapped the previous kernel's tail; global memory is touched below
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -386,7 +387,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, in
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   int grid = tiles < max_ctas ? tiles : max_ctas;
-  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, splits, ep);
+  pdl_launch(kern, dim3(grid), dim3(kThreads), Cfg<BN>::kSmemBytes, stream, ta, tb, M, N, K, splits, ep);
   return LAUNCH_CHECK();
 }
 

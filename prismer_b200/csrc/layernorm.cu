@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 ln_fwd_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
               bf16* __restrict__ y, long long ldy, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
               int D, float eps) {
+  PDL_GRID_SYNC();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   for (long long row = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + warp; row < rows;
@@ -70,6 +71,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restric
               bf16* __restrict__ dz, long long lddz, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows,
               int D, float drop_p, uint32_t thr16, const unsigned long long* seed, uint32_t rng_stream) {
   extern __shared__ float red[];  // [kWarpsPerBlock][2][D] only when dgamma != nullptr
+  PDL_GRID_SYNC();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   float dg[VPL][8], db[VPL][8];
@@ -176,7 +178,7 @@ extern "C" int prismer_layernorm_fwd(const void* x, long long ldx, const float* 
   const bf16* xp = reinterpret_cast<const bf16*>(x);
   bf16* yp = reinterpret_cast<bf16*>(y);
   const int grid = grid_for(rows), block = kWarpsPerBlock * 32;
-#define LN_FWD(V) ln_fwd_kernel<V><<<grid, block, 0, stream>>>(xp, ldx, gamma, beta, yp, ldy, mean, rstd, rows, D, eps)
+#define LN_FWD(V) pdl_launch(ln_fwd_kernel<V>, dim3(grid), dim3(block), 0, stream, xp, ldx, gamma, beta, yp, ldy, mean, rstd, rows, D, eps)
   switch (vpl) {
     case 1: LN_FWD(1); break;
     case 2: LN_FWD(2); break;
@@ -213,7 +215,7 @@ extern "C" int prismer_layernorm_bwd(const void* dy, long long lddy, const void*
       cudaFuncSetAttribute(ln_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
       configured_##V = (int)smem;                                                                                    \
     }                                                                                                                \
-    ln_bwd_kernel<V><<<grid, block, smem, stream>>>(                                                                 \
+    pdl_launch(ln_bwd_kernel<V>, dim3(grid), dim3(block), smem, stream,                                              \
         reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx, mean, rstd, gamma,           \
         reinterpret_cast<const bf16*>(dres), lddres, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dz), \
         lddz, dgamma, dbeta, rows, D, drop_p, thr16, seed, rng_stream);                                              \
