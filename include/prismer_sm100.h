@@ -233,6 +233,9 @@ typedef struct PrismerBatchedGemmArgs {
   int force_bn;   /* 0 = pick the N tile (64 / 128 / 256) that pads N least; tuning override otherwise */
 } PrismerBatchedGemmArgs;
 int prismer_gemm_bf16_batched(const PrismerBatchedGemmArgs* args, cudaStream_t stream);
+/* EXPERIMENTAL: prismer_gemm_bf16 on CTA pairs (tcgen05.mma.cta_group::2, 256 x BN tile per pair, each CTA loading its half of
+ * both operands); same argument block, no split-K, max_ctas counts pairs.  csrc/gemm2_sm100.cu. */
+int prismer_gemm_bf16_2cta(const PrismerGemmArgs* args, cudaStream_t stream);
 /* in place row softmax of bf16 scores [rows, ld] over the first Lk columns (padding columns are zeroed). */
 int prismer_softmax_rows(void* s, long long rows, int Lk, int ld, cudaStream_t stream);
 /* delta[(b*H+h)*Lq + q] = sum_d dO*O, tensors addressed as base + b*bs + q*rs + h*d. */

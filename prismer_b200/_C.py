@@ -100,6 +100,8 @@ def _declare(L):
     L.prismer_check_device.restype = c_int
     L.prismer_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
     L.prismer_gemm_bf16.restype = c_int
+    L.prismer_gemm_bf16_2cta.argtypes = [POINTER(GemmArgs), c_void_p]
+    L.prismer_gemm_bf16_2cta.restype = c_int
     L.prismer_gemm_bf16_batched.argtypes = [POINTER(BatchedGemmArgs), c_void_p]
     L.prismer_gemm_bf16_batched.restype = c_int
     for fn in ("prismer_attention_fwd", "prismer_attention_bwd"):

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -33,6 +34,9 @@ def _req_cuda(*ts):
             raise _C.PrismerError("prismer_b200 ops need CUDA tensors (there is no CPU fallback)")
 
 
+GEMM_2CTA = os.environ.get("PRISMER_GEMM_2CTA") == "1"     # EXPERIMENTAL, default off (see gemm())
+
+
 def _ld(t: torch.Tensor) -> int:
     assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), f"need a 2-D row-major view, got {tuple(t.shape)} / {t.stride()}"
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
@@ -43,8 +47,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
          aux_out: Optional[torch.Tensor] = None, aux_in: Optional[torch.Tensor] = None, act_grad=0,
          out: Optional[torch.Tensor] = None, out_dtype=BF16, accumulate: bool = False, alpha: float = 1.0,
          drop_p: float = 0.0, seed: Optional[torch.Tensor] = None, rng_stream: int = 0, force_bn: int = 0,
-         max_ctas: int = 0, force_splits: int = 0) -> torch.Tensor:
-    """C[M,N] = epilogue(alpha * op(A) . op(B)^T); A is [M,K] (or [K,M] if trans_a), B is [N,K] (or [K,N] if trans_b)."""
+         max_ctas: int = 0, force_splits: int = 0, two_cta: Optional[bool] = None) -> torch.Tensor:
+    """C[M,N] = epilogue(alpha * op(A) . op(B)^T); A is [M,K] (or [K,M] if trans_a), B is [N,K] (or [K,N] if trans_b).
+    ``two_cta``: EXPERIMENTAL cta_group::2 kernel (csrc/gemm2_sm100.cu); None = only when PRISMER_GEMM_2CTA=1 and the shape is
+    encoder-sized (M >= 2048, N >= 256, no split-K candidate)."""
     _req_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16
     if trans_a:
@@ -87,14 +93,17 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
         args.seed = seed.data_ptr()
     args.rng_stream = rng_stream
     args.force_bn, args.max_ctas, args.force_splits = force_bn, max_ctas, force_splits
+    if two_cta is None:
+        two_cta = GEMM_2CTA and M >= 2048 and N >= 256 and not accumulate and force_splits <= 1
+    fn = _C.lib().prismer_gemm_bf16_2cta if two_cta else _C.lib().prismer_gemm_bf16
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        check(_C.lib().prismer_gemm_bf16(ctypes.byref(args), _stream()), "gemm_bf16")
+        check(fn(ctypes.byref(args), _stream()), "gemm_bf16")
         e1.record()
         GEMM_PROFILE.append((M, N, K, e0, e1))
         return out
-    check(_C.lib().prismer_gemm_bf16(ctypes.byref(args), _stream()), "gemm_bf16")
+    check(fn(ctypes.byref(args), _stream()), "gemm_bf16")
     return out
 
 

@@ -42,3 +42,27 @@ def test_unfused_attention_matches_fused_and_torch(B, H, S):
     assert _rel(d4[..., 2 * D:].float(), dv.float()) < 2e-2
     assert _rel(d4[..., :D].float(), dq.float()) < 2e-2
     assert _rel(d4[..., D:2 * D].float(), dk.float()) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [(2048, 768, 768, False, False), (8320, 3072, 768, False, False), (8320, 768, 3072, False, True),
+                                           (1000, 520, 200, False, False), (4096, 768, 2048, True, True), (260, 256, 64, False, False)])
+def test_two_cta_gemm_matches_single_cta(M, N, K, ta, tb):
+    """cta_group::2 kernel (csrc/gemm2_sm100.cu) against the validated single-CTA kernel on the same inputs: plain, and with the
+    fused bias + GELU + saved pre-activation + residual epilogue."""
+    from prismer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = torch.randn((K, M) if ta else (M, K), device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((K, N) if tb else (N, K), device="cuda", generator=g).to(torch.bfloat16)
+    want = ops.gemm(a, b, trans_a=ta, trans_b=tb, two_cta=False)
+    got = ops.gemm(a, b, trans_a=ta, trans_b=tb, two_cta=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)                       # same MMA order over K, same epilogue arithmetic -> bit-identical
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    z1, z2 = torch.empty_like(res), torch.empty_like(res)
+    want = ops.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, act="gelu", aux_out=z1, residual=res, two_cta=False)
+    got = ops.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias, act="gelu", aux_out=z2, residual=res, two_cta=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want) and torch.equal(z1, z2)
+    f32 = ops.gemm(a, b, trans_a=ta, trans_b=tb, out_dtype=torch.float32, two_cta=True)
+    assert _rel(f32, ops.gemm(a, b, trans_a=ta, trans_b=tb, out_dtype=torch.float32, two_cta=False)) < 1e-6
