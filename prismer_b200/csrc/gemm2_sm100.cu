@@ -137,6 +137,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 2 * kNumEpiWarps); }
     ptx::fence_barrier_init();
   }
+  __syncwarp();                                           // warp 0 reconverges: the cluster barrier instructions are .aligned
   ptx2::cluster_sync();                                   // both CTAs' barriers exist before any remote arrive / TMA completion
   if (warp == 1) ptx2::tmem_alloc<C::kTmemCols>(tmem_slot);
   ptx::tc_fence_before();
@@ -384,6 +385,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   // neither CTA may leave (or free TMEM) while the other can still read its shared memory or signal its barriers
   ptx::tc_fence_before();
+  __syncwarp();                                           // producer / MMA lanes rejoin their warps (.aligned barrier below)
   ptx2::cluster_sync();
   if (warp == 1) {
     ptx::tc_fence_after();
