@@ -57,8 +57,12 @@ template <int kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(kCols) : "memory");
 }
-// shared::cluster address of `bar` in the pair's leader (even) CTA: clear the peer bit of this CTA's own window address
-__device__ __forceinline__ uint32_t leader_addr(const void* p) { return ptx::smem_u32(p) & 0xFEFFFFFFu; }
+// shared::cluster address of the object at `p`'s offset in the pair's leader CTA (rank 0)
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(ptx::smem_u32(p)), "r"(0u));
+  return r;
+}
 // 2-D tiled load into THIS CTA's smem, completing transaction bytes on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
