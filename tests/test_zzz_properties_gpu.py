@@ -73,23 +73,26 @@ def test_gradient_is_additive_over_the_batch(base):
     from prismer_b200 import engine
     m, ex, ids, mask = base
     labels = ids.masked_fill(ids == 1, -100); labels[:, :4] = -100
-    st = engine._store(m)
+    # every trainable parameter outside the BatchNorm stems: the stem backward always uses the train-mode (batch-statistics)
+    # BatchNorm formula -- what every reference training script runs -- which couples the samples of a batch by construction
+    names = [n for n, p in m.named_parameters() if p.requires_grad and not ("conv1." in n and "conv1.rgb" not in n)]
+    params = dict(m.named_parameters())
 
     def grad(idx):
         random.seed(11)                                   # same instance-embedding draw for every sub-batch (ids 0..4 present in all)
         loss = engine.train_loss(m, _take(ex, idx), ids[idx], mask[idx], labels[idx])
         loss.backward()
         torch.cuda.synchronize()
-        return st.grad_t.clone(), float(loss)
+        return torch.cat([params[n].grad.reshape(-1).float() for n in names]), float(loss)
 
     full, lf = grad(torch.arange(B, device="cuda"))
     a, la = grad(torch.arange(0, B // 2, device="cuda"))
     b, lb = grad(torch.arange(B // 2, B, device="cuda"))
     comb = 0.5 * (a + b)
     err = _rel(comb, full)
-    print(f"batch additivity: loss {lf:.5f} vs {(la + lb) / 2:.5f}; flat gradient rel-L2 {err:.2e} (|g| {float(full.norm()):.3e})")
+    print(f"batch additivity: loss {lf:.5f} vs {(la + lb) / 2:.5f}; gradient rel-L2 {err:.2e} over {full.numel()} elements (|g| {float(full.norm()):.3e})")
     assert abs(lf - (la + lb) / 2) < 1e-3 * abs(lf)
-    assert err < 3e-2                                     # bf16 dgrad / activation rounding differs between the two tilings
+    assert err < 1e-2                                     # per-sample arithmetic is identical; only the fp32 wgrad reduction order differs
 
 
 def test_greedy_is_prefix_consistent(base):
