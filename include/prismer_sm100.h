@@ -191,6 +191,10 @@ int prismer_bn_stats(const void* y, float* acc, long long M, int C, const float*
 int prismer_bn_relu_bwd(const void* dAcol, const void* y, const float* scale, const float* shift, const float* mean,
                         const float* rstd, const float* gamma, void* dn_scratch, void* dy, float* red, float* dgamma,
                         float* dbeta, int B, int H, int W, int C, int ksz, int stride, int Ho, int Wo, cudaStream_t stream);
+/* The same for a BatchNorm that normalised with its running statistics (eval()): dy = gamma*rstd*dn, no batch-mean terms. */
+int prismer_bn_relu_bwd_eval(const void* dAcol, const void* y, const float* scale, const float* shift, const float* mean,
+                             const float* rstd, const float* gamma, void* dn_scratch, void* dy, float* red, float* dgamma,
+                             float* dbeta, int B, int H, int W, int C, int ksz, int stride, int Ho, int Wo, cudaStream_t stream);
 int prismer_conv_weight_pack(const float* w, void* out, int Cout, int Cin, int ksz, int Kpad, cudaStream_t stream);
 int prismer_conv_weight_unpack_grad(const float* dwp, float* grad, int Cout, int Cin, int ksz, int Kpad, cudaStream_t stream);
 int prismer_cast_pad(const float* src, void* dst, long long R, int C, int Cpad, cudaStream_t stream);

@@ -31,6 +31,7 @@ SIGNATURES = {
     "prismer_im2col_nhwc": [P, P, P, P, I, I, I, I, I, I, I, I, P],
     "prismer_bn_stats": [P, P, L, I, P, P, P, P, P, P, P, P, F, F, I, P],
     "prismer_bn_relu_bwd": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
+    "prismer_bn_relu_bwd_eval": [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
     "prismer_conv_weight_pack": [P, P, I, I, I, I, P],
     "prismer_conv_weight_unpack_grad": [P, P, I, I, I, I, P],
     "prismer_cast_pad": [P, P, L, I, I, P],

@@ -301,6 +301,26 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dn, const bf16* __r
   }
 }
 
+// eval-mode BatchNorm (running statistics are constants): dy = gamma*rstd * dn;  dgamma += sum dn*xhat;  dbeta += sum dn
+__global__ void bn_bwd_apply_eval_kernel(const bf16* __restrict__ dn, const float* __restrict__ red, const float* __restrict__ gamma,
+                                         const float* __restrict__ rstd, bf16* __restrict__ dy, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta, long long M, int C) {
+  const int cv = C >> 3;
+  const long long total = M * cv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cv);
+    float g[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dn + i * 8), g);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) g[t] *= gamma[c * 8 + t] * rstd[c * 8 + t];
+    *reinterpret_cast<bf16x8*>(dy + i * 8) = pack8(g);
+  }
+  if (blockIdx.x == 0 && dgamma) {
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) { dgamma[ch] += red[C + ch]; dbeta[ch] += red[ch]; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- conv weight layouts
 // w fp32 [Cout, Cin, k, k] (reference layout) -> bf16 [Cout, Kpad] with K order (kh, kw, c), zero padded
 __global__ void conv_weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int ksz, int Kpad) {
@@ -420,6 +440,26 @@ extern "C" int prismer_bn_relu_bwd(const void* dAcol, const void* y, const float
   bn_bwd_apply_kernel<<<blocks_for(M * (C / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dn_scratch),
                                                                        reinterpret_cast<const bf16*>(y), red, gamma, mean, rstd,
                                                                        reinterpret_cast<bf16*>(dy), dgamma, dbeta, M, C);
+  return LAUNCH_CHECK();
+}
+
+// Same as prismer_bn_relu_bwd for a BatchNorm that ran on its running statistics (module in eval()): nn.BatchNorm2d's eval-mode
+// gradient has no batch-mean terms.
+extern "C" int prismer_bn_relu_bwd_eval(const void* dAcol, const void* y, const float* scale, const float* shift, const float* mean,
+                                        const float* rstd, const float* gamma, void* dn_scratch, void* dy, float* red, float* dgamma,
+                                        float* dbeta, int B, int H, int W, int C, int ksz, int stride, int Ho, int Wo,
+                                        cudaStream_t stream) {
+  if (C % 8 || C / 8 > 256 || (ksz != 1 && ksz != 3)) return PRISMER_ERR_SHAPE;
+  if (cudaMemsetAsync(red, 0, sizeof(float) * 2 * C, stream) != cudaSuccess) return PRISMER_ERR_CUDA;
+  const long long M = static_cast<long long>(B) * H * W;
+  const int lanes = 256 / (C / 8);
+  long long blocks = (M + lanes - 1) / lanes;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_relu_bwd_gather_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(dAcol), reinterpret_cast<const bf16*>(y), scale, shift, mean, rstd,
+      reinterpret_cast<bf16*>(dn_scratch), red, B, H, W, C, ksz, stride, Ho, Wo);
+  bn_bwd_apply_eval_kernel<<<blocks_for(M * (C / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dn_scratch), red, gamma, rstd,
+                                                                            reinterpret_cast<bf16*>(dy), dgamma, dbeta, M, C);
   return LAUNCH_CHECK();
 }
 

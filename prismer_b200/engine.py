@@ -351,7 +351,7 @@ def _stem_fwd(stem, x, training: bool, save: bool):
         cur, H, W, C = y, Ho, Wo, conv.weight.shape[0]
     A5, _, _ = ops.im2col_nhwc(cur, B, H, W, C, 1, 1, scale, shift)
     tok = gemm(A5, stem["13"].weight._pack16)
-    return tok, H, W, SimpleNamespace(layers=layers, A5=A5 if save else None, B=B)
+    return tok, H, W, SimpleNamespace(layers=layers, A5=A5 if save else None, B=B, training=training)
 
 
 def _stem_bwd(stem, sv, dtok):
@@ -368,7 +368,7 @@ def _stem_bwd(stem, sv, dtok):
         Cout = conv.weight.shape[0]
         tr = bn.weight.requires_grad
         dy = ops.bn_relu_bwd(dA, L.y, L.scale, L.shift, L.mean, L.rstd, bn.weight.data, bn.weight._g32 if tr else None,
-                             bn.bias._g32 if tr else None, B, L.Ho, L.Wo, Cout, ksz, s_next, Ho, Wo)
+                             bn.bias._g32 if tr else None, B, L.Ho, L.Wo, Cout, ksz, s_next, Ho, Wo, training=sv.training)
         if getattr(sv, "debug", False):
             L.dy, L.dA = dy, dA
         if conv.weight.requires_grad:

@@ -391,12 +391,14 @@ def bn_stats(y2d, bn, training: bool):
     return st[0], st[1], st[2], st[3]
 
 
-def bn_relu_bwd(dAcol, y2d, scale, shift, mean, rstd, gamma, dgamma, dbeta, B, H, W, C, ksz, stride, Ho, Wo):
+def bn_relu_bwd(dAcol, y2d, scale, shift, mean, rstd, gamma, dgamma, dbeta, B, H, W, C, ksz, stride, Ho, Wo, training=True):
+    """``training=False``: the BatchNorm ran on its running statistics (eval()) -> gradient without the batch-mean terms."""
     M = B * H * W
     dn = torch.empty((M, C), dtype=BF16, device=y2d.device)
     dy = torch.empty((M, C), dtype=BF16, device=y2d.device)
     red = torch.empty((2, C), dtype=F32, device=y2d.device)
-    check(_C.lib().prismer_bn_relu_bwd(dAcol.data_ptr(), y2d.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+    fn = _C.lib().prismer_bn_relu_bwd if training else _C.lib().prismer_bn_relu_bwd_eval
+    check(fn(dAcol.data_ptr(), y2d.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
                                        rstd.data_ptr(), gamma.data_ptr(), dn.data_ptr(), dy.data_ptr(), red.data_ptr(), _p(dgamma),
                                        _p(dbeta), B, H, W, C, ksz, stride, Ho, Wo, _stream()), "bn_relu_bwd")
     return dy
