@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 
 EXPERTS = ["depth", "normal", "seg_coco", "edge", "obj_detection", "ocr_detection"]
 TRAIN_GFLOP_PER_IMG = 263.1      # BASELINE.md section 3 / SURVEY.md section 8d (freeze_vision, T = 30)
+# secondary row (the reference's real setting image_resolution 480, S = 964): fwd 295.2 G (ViT 225.3, stems
+# 16.3, resampler 15.7, decoder 35.6, LM head 2.35); step = 3 x fwd - 163.8 (frozen ViT wgrad) = 721.8 GFLOP/img
+TRAIN_GFLOP_PER_IMG_480 = 721.8
 FWD_GFLOP_PER_IMG = 102.4
 
 
@@ -84,12 +87,12 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
-def build_inputs(batch, seed, T=30, compact=False):
+def build_inputs(batch, seed, T=30, compact=False, resolution=224):
     from prismer_b200 import synthetic
     if compact:     # uint8 label maps + tables (prismer_b200/data.py) instead of the reference's fp32 stacks
-        ex = synthetic.synth_compact_experts(batch, 224, EXPERTS, 224, seed)
+        ex = synthetic.synth_compact_experts(batch, resolution, EXPERTS, 224, seed)
     else:
-        ex = synthetic.synth_experts(batch, 224, EXPERTS, 224, seed)
+        ex = synthetic.synth_experts(batch, resolution, EXPERTS, 224, seed)
     ids, mask = synthetic.synth_tokens(batch, T, 50265, seed)
     return ex, ids, mask
 
@@ -125,14 +128,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(0)
-    cfg = {"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": 224, "freeze": "freeze_vision"}
+    cfg = {"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": args.resolution, "freeze": "freeze_vision"}
     model = PrismerCaption(cfg)
     model.to(dev)
     st = engine.prepare(model, dev)
     if world > 1:
         dist.broadcast(st.master_t, 0); dist.broadcast(st.master_f, 0); st.refresh(force=True)
     opt = FusedAdamW(model, lr=5e-5, weight_decay=0.05, grad_scale=1.0 / world)
-    ex_h, ids_h, mask_h = build_inputs(B, 1000 + rank, compact=args.compact_inputs)
+    ex_h, ids_h, mask_h = build_inputs(B, 1000 + rank, compact=args.compact_inputs, resolution=args.resolution)
     ex_h = pin(ex_h); ids_h, mask_h = ids_h.pin_memory(), mask_h.pin_memory()
     ex_d = synthetic.experts_to(ex_h, dev); ids_d, mask_d = ids_h.to(dev), mask_h.to(dev)
     h2d = nbytes(ex_h) + ids_h.numel() * 8 + mask_h.numel() * 8
@@ -283,11 +286,12 @@ def run_ours(args):
     ms_step = ms / args.steps
     ips = world * B / (ms_step / 1e3)
     achieved = g_flop / (g_ms / 1e3) / 1e12
+    gflop_img = TRAIN_GFLOP_PER_IMG if args.resolution == 224 else TRAIN_GFLOP_PER_IMG_480
     out = {
         "metric": "Prismer-BASE caption-train images/sec", "value": round(ips, 2), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Prismer-BASE caption fine-tune step (fwd+bwd+1 grad all-reduce+AdamW), 224x224 + 6 expert maps, "
+        "config": {"workload": f"Prismer-BASE caption fine-tune step (fwd+bwd+1 grad all-reduce+AdamW), {args.resolution}x{args.resolution} + 6 expert maps, "
                                "T=30, freeze_vision, dropout 0.1", "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": ("activations written and re-read by one step (> 10 GB/GPU) exceed the 126 MB L2" if args.compact_inputs
                                                        else "per-step inputs (1.28 GB/GPU) exceed the 126 MB L2"),
@@ -307,14 +311,14 @@ def run_ours(args):
                      "note": "achieved = sum(2MNK)/sum(CUDA-event time) over all 623 GEMM launches of one eager step (half of them are "
                              "decoder GEMMs with M = 960 rows, launch/latency bound); large shapes run at 850-1000 TFLOP/s "
                              "(tools/bench_gemm.py)"},
-        "step_mfu": {"model_gflop_per_img": TRAIN_GFLOP_PER_IMG, "achieved_tflops_per_gpu": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3, 1),
-                     "frac_of_peak": round(TRAIN_GFLOP_PER_IMG * ips / world / 1e3 / pk["bf16_tflops_sustained"], 4)},
+        "step_mfu": {"model_gflop_per_img": gflop_img, "achieved_tflops_per_gpu": round(gflop_img * ips / world / 1e3, 1),
+                     "frac_of_peak": round(gflop_img * ips / world / 1e3 / pk["bf16_tflops_sustained"], 4)},
         "host_enqueue_ms_per_step": round(host_ms, 2),
         "entry_point_ms_per_step": kernel_ms,
         "loss": float(loss),
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_train_baseline(model, sample_batch=2, iters=2)
+        out["cpu_baseline"] = cpu_train_baseline(model, sample_batch=2, iters=2, resolution=args.resolution)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -406,7 +410,7 @@ def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):
 
 
 # ----------------------------------------------------------------------------------------------------------- CPU arms
-def cpu_train_baseline(model, sample_batch=2, iters=2, threads=None):
+def cpu_train_baseline(model, sample_batch=2, iters=2, threads=None, resolution=224):
     """The reference's CPU PyTorch path (oracle port: same modules' math, fp32, eager) on a bounded sample of the workload."""
     from oracle import prismer_oracle as O
     # all the host threads eager PyTorch can use productively: beyond ~32 threads the small per-op work of this path is
@@ -414,7 +418,7 @@ def cpu_train_baseline(model, sample_batch=2, iters=2, threads=None):
     threads = threads or min(os.cpu_count() or 1, 32)
     torch.set_num_threads(threads)
     sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
-    ex, ids, mask = build_inputs(sample_batch, 7)
+    ex, ids, mask = build_inputs(sample_batch, 7, resolution=resolution)
     train_keys = {n for n, p in model.named_parameters() if p.requires_grad}
     for k, v in sd.items():
         if k in train_keys:
@@ -438,11 +442,11 @@ def run_reference(args):
         return
     from prismer_b200.prismer_caption import PrismerCaption
     torch.manual_seed(0)
-    cfg = {"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": 224, "freeze": "freeze_vision"}
+    cfg = {"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": args.resolution, "freeze": "freeze_vision"}
     model = PrismerCaption(cfg)          # parameter container only (CPU); the arithmetic below is the oracle port
     sb = 2
     t0 = time.time()
-    base = cpu_train_baseline(model, sample_batch=sb, iters=max(1, min(args.steps, 3)))
+    base = cpu_train_baseline(model, sample_batch=sb, iters=max(1, min(args.steps, 3)), resolution=args.resolution)
     ips = base["value"]
     print(json.dumps({"impl": "reference", "metric": "Prismer-BASE caption-train images/sec", "value": ips, "unit": "images/s",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sb / ips, 1),
@@ -464,6 +468,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph: launch every kernel of the step from Python")
+    ap.add_argument("--resolution", type=int, default=224, choices=[224, 480],
+                    help="rgb resolution: 224 = BASELINE.json's configuration (default), 480 = the reference's configs/caption.yaml (secondary row)")
     ap.add_argument("--compact-inputs", action="store_true",
                     help="feed uint8 label maps + tables (prismer_b200.data) instead of the reference's fp32 expert stacks")
     args = ap.parse_args()
