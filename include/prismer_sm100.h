@@ -237,6 +237,12 @@ typedef struct PrismerBatchedGemmArgs {
   int force_bn;   /* 0 = pick the N tile (64 / 128 / 256) that pads N least; tuning override otherwise */
 } PrismerBatchedGemmArgs;
 int prismer_gemm_bf16_batched(const PrismerBatchedGemmArgs* args, cudaStream_t stream);
+/* EXPERIMENTAL: register-lean prismer_layernorm_bwd (inputs kept packed, dgamma/dbeta accumulated in shared memory or skipped when
+ * NULL): 2-3 resident blocks per SM instead of 1.  Same signature and arithmetic; D <= 1024.  csrc/layernorm_v2.cu. */
+int prismer_layernorm_bwd_v2(const void* dy, long long lddy, const void* x, long long ldx, const float* mean, const float* rstd,
+                             const float* gamma, const void* dres, long long lddres, void* dx, long long lddx, void* dz,
+                             long long lddz, float* dgamma, float* dbeta, int rows, int D, float drop_p,
+                             const unsigned long long* seed, uint32_t rng_stream, cudaStream_t stream);
 /* EXPERIMENTAL: prismer_gemm_bf16 on CTA pairs (tcgen05.mma.cta_group::2, 256 x BN tile per pair, each CTA loading its half of
  * both operands); same argument block, no split-K, max_ctas counts pairs.  csrc/gemm2_sm100.cu. */
 int prismer_gemm_bf16_2cta(const PrismerGemmArgs* args, cudaStream_t stream);

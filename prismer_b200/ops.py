@@ -124,15 +124,19 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return (y.view(x.shape) if out is None else y), mean, rstd
 
 
+LN_BWD_V2 = os.environ.get("PRISMER_LN_BWD_V2") == "1"       # EXPERIMENTAL register-lean backward (csrc/layernorm_v2.cu), default off
+
+
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, dgamma=None, dbeta=None, need_dx=True, dz=False,
-                  drop_p: float = 0.0, seed=None, rng_stream: int = 0):
+                  drop_p: float = 0.0, seed=None, rng_stream: int = 0, v2=None):
     D = x.shape[-1]
     dy2, x2 = dy.reshape(-1, D), x.reshape(-1, D)
     rows = x2.shape[0]
     dx = torch.empty_like(x2) if need_dx else None
     dzt = torch.empty_like(x2) if dz else None
     dres2 = dres.reshape(-1, D) if dres is not None else None
-    check(_C.lib().prismer_layernorm_bwd(dy2.data_ptr(), _ld(dy2), x2.data_ptr(), _ld(x2), mean.data_ptr(), rstd.data_ptr(),
+    fn = _C.lib().prismer_layernorm_bwd_v2 if (LN_BWD_V2 if v2 is None else v2) and D <= 1024 else _C.lib().prismer_layernorm_bwd
+    check(fn(dy2.data_ptr(), _ld(dy2), x2.data_ptr(), _ld(x2), mean.data_ptr(), rstd.data_ptr(),
                                          gamma.data_ptr(), _p(dres2), _ld(dres2) if dres2 is not None else 0,
                                          _p(dx), _ld(dx) if dx is not None else 0, _p(dzt), _ld(dzt) if dzt is not None else 0,
                                          _p(dgamma), _p(dbeta), rows, D, drop_p, _p(seed), rng_stream, _stream()),

@@ -66,3 +66,35 @@ def test_two_cta_gemm_matches_single_cta(M, N, K, ta, tb):
     assert torch.equal(got, want) and torch.equal(z1, z2)
     f32 = ops.gemm(a, b, trans_a=ta, trans_b=tb, out_dtype=torch.float32, two_cta=True)
     assert _rel(f32, ops.gemm(a, b, trans_a=ta, trans_b=tb, out_dtype=torch.float32, two_cta=False)) < 1e-6
+
+
+@pytest.mark.parametrize("rows,D,train_ln,with_res,drop", [(8320, 768, True, True, 0.0), (8320, 768, False, False, 0.0), (960, 768, True, True, 0.1),
+                                                            (1030, 1024, True, False, 0.0), (77, 256, False, True, 0.0)])
+def test_layernorm_bwd_v2_matches_v1(rows, D, train_ln, with_res, drop):
+    """Register-lean LayerNorm backward (csrc/layernorm_v2.cu) against the validated kernel: dx / dz identical up to one bf16 ulp
+    (same arithmetic), dgamma / dbeta up to fp32 summation order."""
+    from prismer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(rows, D, device="cuda", generator=g).to(torch.bfloat16)
+    gamma = torch.randn(D, device="cuda", generator=g)
+    beta = torch.randn(D, device="cuda", generator=g)
+    _, mean, rstd = ops.layernorm_fwd(x, gamma, beta, 1e-5, save_stats=True)
+    dres = torch.randn(rows, D, device="cuda", generator=g).to(torch.bfloat16) if with_res else None
+    seed = torch.tensor([1234], dtype=torch.int64, device="cuda")
+    outs = []
+    for v2 in (False, True):
+        dg = torch.zeros(D, device="cuda") if train_ln else None
+        db = torch.zeros(D, device="cuda") if train_ln else None
+        dx, dz = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dres=dres, dgamma=dg, dbeta=db, dz=drop > 0, drop_p=drop,
+                                   seed=seed if drop > 0 else None, rng_stream=7, v2=v2)
+        torch.cuda.synchronize()
+        outs.append((dx, dz, dg, db))
+    (dx1, dz1, dg1, db1), (dx2, dz2, dg2, db2) = outs
+    ulp = lambda a, b: float(((a.float() - b.float()).abs() / b.float().abs().clamp_min(1e-2)).max())
+    print(f"ln_bwd v2 vs v1 rows={rows} D={D}: dx bit-identical {bool(torch.equal(dx1, dx2))}, max rel {ulp(dx2, dx1):.2e}")
+    assert ulp(dx2, dx1) <= 2 ** -7
+    if dz1 is not None:
+        assert ulp(dz2, dz1) <= 2 ** -7
+    if train_ln:
+        assert _rel(dg2, dg1) < 1e-5 and _rel(db2, db1) < 1e-5
