@@ -149,13 +149,17 @@ def run_ours(args):
     labels_h = labels_d.cpu().pin_memory()
     graphed = None
     if not args.eager:
-        graphed = engine.GraphedTrainStep(model, ex_d, ids_d, mask_d, labels_d, overlap=world > 1)
+        graphed = engine.GraphedTrainStep(model, ex_d, ids_d, mask_d, labels_d, overlap=world > 1 or args.overlap_optimizer)
     comm = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)) if world > 1 else None
 
     def step(ex, ids, mask, host_inputs=False):
         if graphed is not None:
             if host_inputs:                                  # pinned host -> static device buffers (H2D inside the step)
                 graphed.load_inputs(ex, ids, mask, labels_h)
+            if args.overlap_optimizer:                       # experiment: AdamW of the decoder slice overlaps the encoder backward
+                loss = graphed(comm, on_decoder_grads=lambda: opt.step_range(0, st.n_train_dec, True, False))
+                opt.step_range(st.n_train_dec, st.n_train, False, True)
+                return loss
             loss = graphed(comm)                             # fwd + bwd as CUDA graph(s); grads all-reduced, decoder slice early
             opt.step()
             return loss
@@ -468,6 +472,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph: launch every kernel of the step from Python")
+    ap.add_argument("--overlap-optimizer", action="store_true",
+                    help="experiment: two-graph step; AdamW of the decoder slice runs on a side stream during the encoder backward")
     ap.add_argument("--resolution", type=int, default=224, choices=[224, 480],
                     help="rgb resolution: 224 = BASELINE.json's configuration (default), 480 = the reference's configs/caption.yaml (secondary row)")
     ap.add_argument("--compact-inputs", action="store_true",

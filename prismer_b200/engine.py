@@ -1114,21 +1114,35 @@ class GraphedTrainStep:
         if weights is not None:
             self.weights.copy_(weights, non_blocking=non_blocking)
 
-    def __call__(self, comm=None) -> torch.Tensor:
+    def __call__(self, comm=None, on_decoder_grads=None) -> torch.Tensor:
         """Replay on the current static inputs; returns the (device, 1-element) batch-mean loss.
         ``comm(tensor) -> handle with .wait()`` (e.g. ``lambda t: dist.all_reduce(t, async_op=True)``): with ``overlap=True`` it
-        is called on the decoder slice of the flat gradients right after graph 1 and on the rest after graph 2."""
+        is called on the decoder slice of the flat gradients right after graph 1 and on the rest after graph 2.
+        ``on_decoder_grads()`` (overlap only): called on a side stream once the decoder slice is final (after its all-reduce) while
+        graph 2 -- the encoder backward -- runs on the main stream, e.g. the optimizer update of that slice; joined before return."""
         self.store.refresh()
         self._draw_table()
         self.graph.replay()
         if self.overlap:
             st = self.store
             h1 = comm(st.grad_t[:st.n_train_dec]) if comm is not None else None
+            if on_decoder_grads is not None:
+                main = torch.cuda.current_stream()
+                if getattr(self, "_opt_stream", None) is None:
+                    self._opt_stream = torch.cuda.Stream(device=st.device)
+                self._opt_stream.wait_stream(main)
+                with torch.cuda.stream(self._opt_stream):
+                    if h1 is not None:
+                        h1.wait()
+                        h1 = None
+                    on_decoder_grads()
             self.graph2.replay()
             h2 = comm(st.grad_t[st.n_train_dec:]) if comm is not None else None
             for h in (h1, h2):
                 if h is not None:
                     h.wait()
+            if on_decoder_grads is not None:
+                torch.cuda.current_stream().wait_stream(self._opt_stream)
         elif comm is not None:
             comm(self.store.grad_t).wait()
         return self.loss

@@ -34,6 +34,22 @@ class FusedAdamW:
                        g["weight_decay"], self.t, self.grad_scale)
         st.mark_fresh()
 
+    @torch.no_grad()
+    def step_range(self, lo: int, hi: int, first: bool, last: bool):
+        """The update restricted to elements [lo, hi) of the flat buffers (multiples of 8).  A data-parallel / graphed caller can
+        update the decoder slice [0, store.n_train_dec) as soon as its gradients are final -- on another stream, while the encoder
+        backward is still running -- and the rest afterwards: ``first`` advances the step count, ``last`` republishes derived
+        weights (conv packs).  step() == step_range(0, n, True, True)."""
+        st = self.store
+        g = self.param_groups[0]
+        if first:
+            self.t += 1
+        if hi > lo:
+            ops.adamw_step(st.master_t[lo:hi], st.grad_t[lo:hi], self.m[lo:hi], self.v[lo:hi], st.c16_t[lo:hi], g["lr"], g["betas"][0],
+                           g["betas"][1], g["eps"], g["weight_decay"], self.t, self.grad_scale)
+        if last:
+            st.mark_fresh()
+
     def state_dict(self):
         return {"m": self.m, "v": self.v, "t": self.t, "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
