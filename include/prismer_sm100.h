@@ -25,6 +25,16 @@ typedef struct CUstream_st* cudaStream_t;
 
 #define PRISMER_ABI_VERSION 1
 
+/* return codes: 0 on success, negative otherwise (never throws, never exits; cudaGetLastError is folded into the result) */
+#ifndef PRISMER_OK
+#define PRISMER_OK 0
+#define PRISMER_ERR_SHAPE -1  /* unsupported / inconsistent dimensions or NULL where a pointer is required */
+#define PRISMER_ERR_ALIGN -2  /* base pointer not 16-byte aligned or leading dimension not a multiple of 8 elements */
+#define PRISMER_ERR_ARCH -3   /* device is not sm_100 */
+#define PRISMER_ERR_CUDA -4   /* a CUDA runtime call or the launch failed */
+#define PRISMER_ERR_DRIVER -5 /* cuTensorMapEncodeTiled unavailable / rejected the tensor map */
+#endif
+
 /* activation codes */
 #define PRISMER_ACT_NONE 0
 #define PRISMER_ACT_QUICKGELU 1 /* model/modules/utils.py:23-25 */

@@ -7,12 +7,14 @@
 
 typedef __nv_bfloat16 bf16;
 
+#ifndef PRISMER_OK      // also published by include/prismer_sm100.h (identical values)
 #define PRISMER_OK 0
 #define PRISMER_ERR_SHAPE -1
 #define PRISMER_ERR_ALIGN -2
 #define PRISMER_ERR_ARCH -3
 #define PRISMER_ERR_CUDA -4
 #define PRISMER_ERR_DRIVER -5
+#endif
 
 // activation codes used across the C-ABI
 enum : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_GELU = 2, ACT_SQRELU = 3, ACT_RELU = 4 };
