@@ -561,32 +561,44 @@ def _unfused_attn_fwd(qkv, o, B, S, H, save):
     return P if save else None
 
 
-def _unfused_attn_bwd(do, qkv, o, P, dqkv, B, S, H):
-    """``P``: the probabilities saved by ``_unfused_attn_fwd`` ([B*H, S, Sp] bf16), or the fused forward's LSE ([B, H, S] fp32),
-    from which they are recomputed: P = exp(scale * Q K^T - lse) in the score GEMM's epilogue."""
-    D = o.shape[1]
-    d = D // H
-    ld = B * 3 * D
-    if P.dtype == F32:
-        lse, Sp = P, (S + 7) // 8 * 8
-        P = torch.empty((B * H, S, Sp), dtype=BF16, device=qkv.device)
-        ops.gemm_batched(qkv, qkv[:, D:], P, S, S, d, lda=ld, ldb=ld, ldc=Sp, batch_outer=B, batch_inner=H, a_bs=(3 * D, d),
-                         b_bs=(3 * D, d), c_bs=(H * S * Sp, S * Sp), rowvec=lse, rowvec_bs=S, mode=2, alpha=d ** -0.5)
-    Sp = P.shape[2]
-    qs, ps, os_ = (3 * D, d), (H * S * Sp, S * Sp), (D, d)
-    delta = ops.attn_delta(do, o, B, H, S, d)
-    # dV = P^T dO
-    ops.gemm_batched(P, do, dqkv[:, 2 * D:], S, d, S, lda=Sp, ldb=B * D, ldc=ld, trans_a=True, trans_b=True, batch_outer=B, batch_inner=H,
-                     a_bs=ps, b_bs=os_, c_bs=qs)
+def _gemm_attn_bwd(do, o, q, k, v, saved, dq, dk, dv, B, H, Lq, Lk):
+    """Attention backward as batched tcgen05 GEMMs over (batch, head) -- no mask, no dropout.  Every tensor is a seq-first 2-D view
+    [L*B, H*d] (rows l*B + b), possibly a column slice of a packed projection buffer (its row stride is taken from the view).
+    ``saved``: the probabilities [B*H, Lq, Lkp] bf16 kept by ``_unfused_attn_fwd``, or the fused forward's LSE [B, H, Lq] fp32, from
+    which they are recomputed in the score GEMM's epilogue: P = exp(scale * Q K^T - lse)."""
+    d = o.shape[1] // H
+    scale = d ** -0.5
+    lay = lambda t: (B * t.stride(0), (t.stride(0), d))            # (leading dimension, (batch stride, head stride)) of a seq-first view
+    (ldq, qs), (ldk, ks), (ldv, vs), (ldo, os_), (lddo, dos) = lay(q), lay(k), lay(v), lay(o), lay(do)
+    (lddq, dqs), (lddk, dks), (lddv, dvs) = lay(dq), lay(dk), lay(dv)
+    if saved.dtype == F32:
+        Lkp = (Lk + 7) // 8 * 8
+        P = torch.empty((B * H, Lq, Lkp), dtype=BF16, device=q.device)
+        ops.gemm_batched(q, k, P, Lq, Lk, d, lda=ldq, ldb=ldk, ldc=Lkp, batch_outer=B, batch_inner=H, a_bs=qs, b_bs=ks,
+                         c_bs=(H * Lq * Lkp, Lq * Lkp), rowvec=saved, rowvec_bs=Lq, mode=2, alpha=scale)
+    else:
+        P = saved
+    Lkp = P.shape[2]
+    ps = (H * Lq * Lkp, Lq * Lkp)
+    delta = ops.attn_delta(do, o, B, H, Lq, d) if (ldo == lddo and os_ == dos) else None
+    assert delta is not None, "dO and O must share their layout"
+    # dV = P^T dO                                                  [Lk, d] = [Lq, Lk]^T [Lq, d]
+    ops.gemm_batched(P, do, dv, Lk, d, Lq, lda=Lkp, ldb=lddo, ldc=lddv, trans_a=True, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps,
+                     b_bs=dos, c_bs=dvs)
     # dS = P * (dO V^T - delta) * scale   (softmax backward fused into the epilogue)
     dS = torch.empty_like(P)
-    ops.gemm_batched(do, qkv[:, 2 * D:], dS, S, S, d, lda=B * D, ldb=ld, ldc=Sp, batch_outer=B, batch_inner=H, a_bs=os_, b_bs=qs, c_bs=ps,
-                     aux=P, ldaux=Sp, aux_bs=ps, rowvec=delta, rowvec_bs=S, mode=1, alpha=d ** -0.5)
+    ops.gemm_batched(do, v, dS, Lq, Lk, d, lda=lddo, ldb=ldv, ldc=Lkp, batch_outer=B, batch_inner=H, a_bs=dos, b_bs=vs, c_bs=ps, aux=P,
+                     ldaux=Lkp, aux_bs=ps, rowvec=delta, rowvec_bs=Lq, mode=1, alpha=scale)
     # dQ = dS K ; dK = dS^T Q
-    ops.gemm_batched(dS, qkv[:, D:], dqkv, S, d, S, lda=Sp, ldb=ld, ldc=ld, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps, b_bs=qs,
-                     c_bs=qs)
-    ops.gemm_batched(dS, qkv, dqkv[:, D:], S, d, S, lda=Sp, ldb=ld, ldc=ld, trans_a=True, trans_b=True, batch_outer=B, batch_inner=H,
-                     a_bs=ps, b_bs=qs, c_bs=qs)
+    ops.gemm_batched(dS, k, dq, Lq, d, Lk, lda=Lkp, ldb=ldk, ldc=lddq, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps, b_bs=ks, c_bs=dqs)
+    ops.gemm_batched(dS, q, dk, Lk, d, Lq, lda=Lkp, ldb=ldq, ldc=lddk, trans_a=True, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps,
+                     b_bs=qs, c_bs=dks)
+
+
+def _unfused_attn_bwd(do, qkv, o, P, dqkv, B, S, H):
+    """Self-attention on packed projections [S*B, 3D] (the ViT blocks): see ``_gemm_attn_bwd``."""
+    D = o.shape[1]
+    _gemm_attn_bwd(do, o, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], P, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, H, S, S)
 
 
 def _vit_block_fwd(blk, adp, x, B, S, save):
@@ -680,8 +692,11 @@ def _resampler_bwd(res, svs, dlat, xf, B, N):
         dq = torch.empty_like(sv.q)
         dkv = torch.empty_like(sv.kv)
         kv3, dkv3 = _sf(sv.kv, Lr + N, B), _sf(dkv, Lr + N, B)
-        ops.attention_bwd(_sf(do, Lr, B), _sf(sv.q, Lr, B), kv3[..., :D], kv3[..., D:], _sf(sv.o, Lr, B), sv.lse, H,
-                          dq=_sf(dq, Lr, B), dk=dkv3[..., :D], dv=dkv3[..., D:])
+        if ATTN_UNFUSED_BWD and (D // H) % 32 == 0:              # experimental: batched tcgen05 GEMMs, P recomputed from the LSE
+            _gemm_attn_bwd(do, sv.o, sv.q, sv.kv[:, :D], sv.kv[:, D:], sv.lse, dq, dkv[:, :D], dkv[:, D:], B, H, Lr, Lr + N)
+        else:
+            ops.attention_bwd(_sf(do, Lr, B), _sf(sv.q, Lr, B), kv3[..., :D], kv3[..., D:], _sf(sv.o, Lr, B), sv.lse, H,
+                              dq=_sf(dq, Lr, B), dk=dkv3[..., :D], dv=dkv3[..., D:])
         if at.in_proj_weight.requires_grad:
             wg, bg = at.in_proj_weight._g32, at.in_proj_bias._g32
             _wgrad(dq, sv.kvin[:Lr * B], wg[:D]); _bgrad(dq, bg[:D])

@@ -465,6 +465,7 @@ def softmax_rows(s2d, Lk):
 def attn_delta(dout_sf, o_sf, B, H, Lq, d):
     """dout / o: seq-first [Lq*B, H*d] rows (l*B + b).  Returns delta fp32 [B*H, Lq]."""
     delta = torch.empty((B * H, Lq), dtype=F32, device=o_sf.device)
-    D = H * d
-    check(_C.lib().prismer_attn_delta(dout_sf.data_ptr(), o_sf.data_ptr(), D, B * D, delta.data_ptr(), B, H, Lq, d, _stream()), "attn_delta")
+    W = o_sf.stride(0)                                   # row width of the (possibly packed) buffer both views live in
+    assert dout_sf.stride(0) == W and o_sf.stride(1) == 1 and dout_sf.stride(1) == 1
+    check(_C.lib().prismer_attn_delta(dout_sf.data_ptr(), o_sf.data_ptr(), W, B * W, delta.data_ptr(), B, H, Lq, d, _stream()), "attn_delta")
     return delta

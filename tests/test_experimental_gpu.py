@@ -98,3 +98,25 @@ def test_layernorm_bwd_v2_matches_v1(rows, D, train_ln, with_res, drop):
         assert ulp(dz2, dz1) <= 2 ** -7
     if train_ln:
         assert _rel(dg2, dg1) < 1e-5 and _rel(db2, db1) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d", [(4, 8, 64, 1240, 96), (2, 12, 30, 260, 64)])
+def test_gemm_attention_backward_cross_shapes(B, H, Lq, Lk, d):
+    """Resampler-shaped (Lq = 64 latents, Lk = 64 + 1176, d = 96) backward through the batched GEMMs vs the fused kernel."""
+    from prismer_b200 import engine, ops
+    D = H * d
+    g = torch.Generator(device="cuda").manual_seed(Lk)
+    qb = (0.5 * torch.randn(Lq * B, D, device="cuda", generator=g)).to(torch.bfloat16)
+    kvb = (0.5 * torch.randn(Lk * B, 2 * D, device="cuda", generator=g)).to(torch.bfloat16)
+    do = torch.randn(Lq * B, D, device="cuda", generator=g).to(torch.bfloat16)
+    q3, kv3 = engine._sf(qb, Lq, B), engine._sf(kvb, Lk, B)
+    o = torch.empty(Lq * B, D, device="cuda", dtype=torch.bfloat16)
+    _, lse = ops.attention_fwd(q3, kv3[..., :D], kv3[..., D:], H, out=engine._sf(o, Lq, B))
+    dq1, dkv1 = torch.empty_like(qb), torch.empty_like(kvb)
+    d3 = engine._sf(dkv1, Lk, B)
+    ops.attention_bwd(engine._sf(do, Lq, B), q3, kv3[..., :D], kv3[..., D:], engine._sf(o, Lq, B), lse, H, dq=engine._sf(dq1, Lq, B),
+                      dk=d3[..., :D], dv=d3[..., D:])
+    dq2, dkv2 = torch.zeros_like(qb), torch.zeros_like(kvb)
+    engine._gemm_attn_bwd(do, o, qb, kvb[:, :D], kvb[:, D:], lse, dq2, dkv2[:, :D], dkv2[:, D:], B, H, Lq, Lk)
+    torch.cuda.synchronize()
+    assert _rel(dq2, dq1) < 2e-2 and _rel(dkv2, dkv1) < 2e-2

@@ -91,3 +91,26 @@ def test_unfused_attention_call_graph_matches_autograd(emulated, B, H, S):
             got = dqkv.view(S, B, 3, H, d)[:, :, i].float()
             want = ref.grad.view(S, B, 3, H, d)[:, :, i]
             assert rel(got, want) < 3e-2, (name, "P" if saved is P else "lse")
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,d", [(2, 2, 8, 29, 96), (1, 3, 5, 12, 64)])
+def test_gemm_attention_backward_general_layouts(emulated, B, H, Lq, Lk, d):
+    """Resampler-shaped cross attention (resampler.py:30-31): q from its own buffer, K | V packed in another, Lq != Lk, d = 96."""
+    D = H * d
+    torch.manual_seed(Lq * Lk)
+    qb = (0.5 * torch.randn(Lq * B, D)).to(torch.bfloat16)
+    kvb = (0.5 * torch.randn(Lk * B, 2 * D)).to(torch.bfloat16)
+    do = torch.randn(Lq * B, D).to(torch.bfloat16)
+    qr, kvr = qb.float().clone().requires_grad_(True), kvb.float().clone().requires_grad_(True)
+    q = qr.view(Lq, B, H, d).permute(1, 2, 0, 3)
+    k = kvr.view(Lk, B, 2, H, d)[:, :, 0].permute(1, 2, 0, 3)
+    v = kvr.view(Lk, B, 2, H, d)[:, :, 1].permute(1, 2, 0, 3)
+    s_ = q @ k.transpose(-1, -2) / math.sqrt(d)
+    o_ref = (torch.softmax(s_, -1) @ v).permute(2, 0, 1, 3).reshape(Lq * B, D)
+    o_ref.backward(do.float())
+    lse = torch.logsumexp(s_, -1).detach().contiguous()
+    o = o_ref.detach().to(torch.bfloat16)
+    dq, dkv = torch.zeros_like(qb), torch.zeros_like(kvb)
+    engine._gemm_attn_bwd(do, o, qb, kvb[:, :D], kvb[:, D:], lse, dq, dkv[:, :D], dkv[:, D:], B, H, Lq, Lk)
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    assert rel(dq, qr.grad) < 3e-2 and rel(dkv, kvr.grad) < 3e-2
