@@ -152,7 +152,7 @@ def beam_search_core(step_logits, input_ids, attention_mask, num_beams, max_leng
         V = lp.shape[-1]
         if cur < min_length:
             lp[:, eos] = -float("inf")                      # MinLengthLogitsProcessor
-        acc = (lp.view(B, nb, V) + run_score[:, :, None]).view(B, nb * V)
+        acc = (lp.reshape(B, nb, V) + run_score[:, :, None]).reshape(B, nb * V)     # (logits may be a strided view of a padded buffer)
         top_s, top_i = acc.topk(K, dim=1)                   # 2*nb continuations: enough live ones survive nb eos hits
         cand = take(run_seq, top_i // V)
         tok = top_i % V
