@@ -1,7 +1,7 @@
 """``PrismerCaption`` -- the call surface of ``model/prismer_caption.py:14-112`` on the sm_100a engine."""
 import torch
 
-from . import engine
+from . import engine, text
 from .prismer import Prismer
 
 
@@ -12,13 +12,13 @@ class PrismerCaption(Prismer):
         the data loader can own tokenisation."""
         device = experts["rgb"].device
         if train:
-            if input_ids is None:
-                tok = self.tokenizer(caption, padding="longest", truncation=True, max_length=30, return_tensors="pt").to(device)
-                input_ids, attention_mask = tok.input_ids, tok.attention_mask
-                prompt_length = len(self.tokenizer(prefix).input_ids) - 1 if len(prefix) > 0 else 0
-            labels = input_ids.masked_fill(input_ids == self.tokenizer.pad_token_id, -100)   # prismer_caption.py:22
-            if prompt_length:
-                labels[:, :prompt_length] = -100                                              # prismer_caption.py:24-26
+            if input_ids is None:                                                             # strings: tokenise here, as the reference
+                input_ids, attention_mask, labels, _ = text.caption_inputs(self.tokenizer, caption, prefix)
+                input_ids, attention_mask, labels = input_ids.to(device), attention_mask.to(device), labels.to(device)
+            else:                                                                             # tensors from the data loader (N3)
+                labels = input_ids.masked_fill(input_ids == self.tokenizer.pad_token_id, -100)    # prismer_caption.py:22
+                if prompt_length:
+                    labels[:, :prompt_length] = -100                                          # prismer_caption.py:24-26
             return engine.train_loss(self, experts, input_ids, attention_mask, labels)
 
         if inference == "generate":

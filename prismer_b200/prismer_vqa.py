@@ -1,26 +1,24 @@
 """``PrismerVQA`` -- the call surface of ``model/prismer_vqa.py:15-113`` on the sm_100a engine."""
 import torch
 
-from . import engine
+from . import engine, text
 from .prismer import Prismer
 from .prismer_caption import rank
 
 
 class PrismerVQA(Prismer):
-    def forward(self, experts, question, answer=None, weights=None, train=True, inference="rank", k_test=128):
+    def forward(self, experts, question=None, answer=None, weights=None, train=True, inference="rank", k_test=128,
+                input_ids=None, attention_mask=None, labels=None):
+        """Reference signature; ``train=True`` additionally accepts pre-tokenised ``input_ids / attention_mask / labels``
+        (``text.vqa_inputs`` run by the data loader) instead of the strings."""
         device = experts["rgb"].device
-        question = ["<s>" + q.capitalize() for q in question]
-        q = self.tokenizer(question, padding="longest", truncation=True, max_length=35, add_special_tokens=False,
-                           return_tensors="pt").to(device)
         if train:
-            a = self.tokenizer([" " + x.capitalize() + "</s>" for x in answer], padding="longest", return_tensors="pt",
-                               add_special_tokens=False).to(device)
-            input_ids = torch.cat([q.input_ids, a.input_ids], dim=1).long()
-            attention_mask = torch.cat([q.attention_mask, a.attention_mask], dim=1)
-            targets = input_ids.masked_fill(input_ids == self.tokenizer.pad_token_id, -100)
-            targets[:, :-a.input_ids.shape[1]] = -100                                   # prismer_vqa.py:32-33
+            if input_ids is None:
+                input_ids, attention_mask, labels = text.vqa_inputs(self.tokenizer, question, answer)    # prismer_vqa.py:18-33
+            input_ids, attention_mask, labels = input_ids.to(device), attention_mask.to(device), labels.to(device)
             w = weights.to(device=device, dtype=torch.float32).contiguous() if weights is not None else None
-            return engine.train_loss(self, experts, input_ids, attention_mask, targets, w)   # mean(weights * loss)
+            return engine.train_loss(self, experts, input_ids, attention_mask, labels, w)               # mean(weights * loss)
+        q = text.vqa_question(self.tokenizer, question).to(device)
         if inference == "generate":
             enc = self.expert_encoder(experts).transpose(0, 1)
             outputs = self.text_decoder.generate(input_ids=q.input_ids, encoder_hidden_states=enc, attention_mask=q.attention_mask,
@@ -29,7 +27,6 @@ class PrismerVQA(Prismer):
             return [self.tokenizer.decode(outputs[i, q.input_ids.shape[1]:], skip_special_tokens=True).lower().strip()
                     for i in range(len(outputs))]
         if inference == "rank":
-            a = self.tokenizer([" " + x.capitalize() + "</s>" for x in answer], padding="longest", return_tensors="pt",
-                               add_special_tokens=False).to(device)
+            a = text.vqa_answers(self.tokenizer, answer).to(device)
             return rank(self, experts, q.input_ids, q.attention_mask, a.input_ids, a.attention_mask, k_test)
         raise ValueError(inference)

@@ -54,3 +54,27 @@ def test_vqa_train_rank_generate(fx):
     r = _run(fx, O.vqa_forward, S["questions"], S["candidates"], train=False, inference="rank", k_test=S["k_test"])
     assert np.array_equal(r.numpy(), g["vqa.rank"])
     assert _run(fx, O.vqa_forward, S["questions"], train=False, inference="generate") == g["vqa.generate"].tolist()
+
+
+def test_host_tokenisation_helpers_reproduce_the_reference_losses(fx):
+    """``prismer_b200.text`` (what the product's ``forward`` and an N3-style data loader call) builds the same ids / masks / labels as
+    the reference's ``forward``: scoring them with the oracle decoder gives the reference's own losses."""
+    from prismer_b200 import text
+    cfg, sd, ex, tok, g = fx
+    esd, dsd = O.split_state_dict(sd)
+    random.seed(cfg["py_seed"])
+    with torch.no_grad():
+        enc = O.encoder_forward(ex, esd, cfg["patch"]).transpose(0, 1)
+        ids, mask, labels, plen = text.caption_inputs(tok, S["captions"], S["prefix"])
+        assert plen == 4 and bool((labels[:, :4] == -100).all()) and ids.shape == mask.shape == labels.shape
+        _, loss = O.decoder_forward(ids, mask, enc, dsd, HEADS, labels)
+        assert abs(float(loss.mean()) - float(g["cap.loss"])) < 2e-5 * float(g["cap.loss"])
+        ids, mask, labels, plen = text.caption_inputs(tok, S["captions"])
+        assert plen == 0
+        _, loss = O.decoder_forward(ids, mask, enc, dsd, HEADS, labels)
+        assert abs(float(loss.mean()) - float(g["cap.loss_noprefix"])) < 2e-5 * float(g["cap.loss_noprefix"])
+        ids, mask, labels = text.vqa_inputs(tok, S["questions"], S["answers"])
+        _, loss = O.decoder_forward(ids, mask, enc, dsd, HEADS, labels)
+        assert abs(float((torch.tensor(S["weights"]) * loss).mean()) - float(g["vqa.loss"])) < 2e-5 * float(g["vqa.loss"])
+    q = text.vqa_question(tok, S["questions"])
+    assert q.input_ids[0, 0] == 0 and int((q.input_ids == 2).sum()) == 0           # <s> prepended, no </s> (prismer_vqa.py:18-20)
