@@ -66,3 +66,33 @@ def test_beam_core_without_prompt_mask_equals_all_ones(template, gold):
     with torch.no_grad():
         out, _ = generation.beam_search_core(step, ids, None, c["nb"], c["T0"] + c["max_add"], c["T0"] + c["min_add"], c["lp"], 2, 1)
     assert np.array_equal(out.numpy(), gold[c["name"] + ".ids"])
+
+
+def test_beam_search_driver_plumbing_with_a_stand_in_engine(template, gold, monkeypatch):
+    """``generation.beam_search`` itself (beam expansion of the visual tokens, one K/V projection per call, last-position logits,
+    prompt mask) with the engine's three entry points replaced by oracle-backed stand-ins: same ids as the reference."""
+    from types import SimpleNamespace
+    from prismer_b200 import engine
+    c = BEAM_CASES[5]                                     # VQA-style: ragged prompts, length_penalty -1
+    sd, ids, mask, enc = _case(c, template, gold)
+    calls = {"kv": 0, "fwd": 0}
+
+    def fake_cross_kv(dec, enc_b):
+        calls["kv"] += 1
+        return SimpleNamespace(B=enc_b.shape[0], enc=enc_b)
+
+    def fake_decoder_forward(dec, input_ids, attention_mask, enc_b, labels, weights, save, kv=None, last_only=False, **_):
+        calls["fwd"] += 1
+        assert kv is not None and last_only and not save and kv.B == input_ids.shape[0] == attention_mask.shape[0]
+        logits, _ = O.decoder_forward(input_ids, attention_mask, kv.enc.float(), sd, HEADS)
+        return logits[:, -1].float(), None, None, None
+
+    monkeypatch.setattr(engine, "cross_kv", fake_cross_kv)
+    monkeypatch.setattr(engine, "decoder_forward", fake_decoder_forward)
+    monkeypatch.setattr(engine, "_store", lambda m: SimpleNamespace(refresh=lambda: None))
+    dec = SimpleNamespace(config=SimpleNamespace(eos_token_id=TINY_DEC["eos_token_id"], pad_token_id=TINY_DEC["pad_token_id"],
+                                                 vocab_size=TINY_DEC["vocab_size"]))
+    out, sc = generation.beam_search(dec, ids, enc, mask, c["nb"], c["T0"] + c["max_add"], c["T0"] + c["min_add"], c["lp"], return_scores=True)
+    assert calls["kv"] == 1 and calls["fwd"] >= 2
+    assert np.array_equal(out.numpy(), gold[c["name"] + ".ids"])
+    np.testing.assert_allclose(sc.numpy(), gold[c["name"] + ".scores"], rtol=2e-6, atol=2e-5)
