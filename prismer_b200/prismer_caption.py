@@ -32,9 +32,9 @@ class PrismerCaption(Prismer):
                 return outputs
             captions = []
             for output in outputs:
-                text = self.tokenizer.decode(output, skip_special_tokens=True)
+                decoded = self.tokenizer.decode(output, skip_special_tokens=True)
                 space_idx = 1 if len(prefix) > 0 else 0
-                captions.append(text[len(prefix) + space_idx:])
+                captions.append(decoded[len(prefix) + space_idx:])
             return captions
 
         if inference == "rank":
