@@ -50,10 +50,8 @@ class CompactMap:
 
     def expand(self) -> torch.Tensor:
         """The reference-format fp32 tensor, built by the CUDA kernel (the map must live on the GPU)."""
-        if not self.u8.is_cuda:
-            raise RuntimeError("CompactMap.expand() runs on the GPU; move the map with .to('cuda') first "
-                               "(expand_on_host() exists for data-loader side checks)")
         from . import ops
+        ops._req_cuda(self.u8, self.table)       # no CPU fallback: raises PrismerError (expand_on_host() exists for data-loader checks)
         batched = self.u8.dim() == 4
         u8 = (self.u8 if batched else self.u8[None]).contiguous()
         out = ops.expand_labels(u8, self.table.contiguous())

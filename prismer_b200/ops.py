@@ -89,7 +89,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
     args.alpha = alpha
     args.drop_p = drop_p
     if drop_p > 0:
-        assert seed is not None and seed.dtype == torch.int64 and seed.is_cuda
+        assert seed is not None and seed.dtype == torch.int64
+        _req_cuda(seed)
         args.seed = seed.data_ptr()
     args.rng_stream = rng_stream
     args.force_bn, args.max_ctas, args.force_splits = force_bn, max_ctas, force_splits
