@@ -139,3 +139,48 @@ def test_optimizer_host_code(dry):
     opt.step_range(st.n_train_dec, st.n_train, False, True)  # ... then the rest: one logical step
     assert opt.t == 2 and dry.calls["prismer_adamw_step"] == 3 and 0 < st.n_train_dec < st.n_train
     assert dry.calls.get("prismer_conv_weight_pack", 0) > 0   # trainable conv weights were re-packed for the next forward
+
+
+@pytest.mark.parametrize("compact,stock_adamw", [(False, False), (True, True)])
+def test_reference_training_loop_host_code(dry, monkeypatch, compact, stock_adamw):
+    """The loop body of train_caption.py:126-133 as examples/train_caption_synthetic.py runs it: dataset -> DataLoader ->
+    accelerator.prepare -> model(experts, caption, prefix=...) -> accelerator.backward -> optimizer.step, then beam-3 generate."""
+    import os
+    from torch.utils.data import DataLoader
+    from prismer_b200.accelerate_shim import Accelerator
+    from prismer_b200.optim import FusedAdamW
+    from prismer_b200.prismer_caption import PrismerCaption
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    tiny = {"roberta_model": dict(TINY_DEC, model_name="roberta-tiny"), "vit_model": "tiny", "vit_dims": [16, 256, 2]}
+    config = {"experts": EXPERTS, "prismer_model": "tiny", "image_resolution": 64, "freeze": "freeze_vision", "prismer_config": tiny,
+              "prefix": "A picture of"}
+    accelerator = Accelerator(mixed_precision="bf16")
+    assert accelerator.device.type == "cpu"                          # no GPU here: the recorder stands in for the CUDA library
+    model = PrismerCaption(config)
+    if stock_adamw:                                                  # train_caption.py:111-117 order: optimizer first, then prepare
+        optimizer = torch.optim.AdamW(params=filter(lambda p: p.requires_grad, model.parameters()), lr=5e-5, weight_decay=0.05)
+        model = accelerator.prepare(model)
+    else:
+        model = accelerator.prepare(model)
+        optimizer = accelerator.prepare(FusedAdamW(model, lr=5e-5, weight_decay=0.05))
+    ds = synthetic.SyntheticCaptionDataset(4, EXPERTS, 64, 64, compact=compact, prefix=config["prefix"])
+    loader = accelerator.prepare(DataLoader(ds, batch_size=2, collate_fn=ds.collate, shuffle=True, drop_last=True))
+    model.train()
+    steps = 0
+    for experts, caption in loader:
+        loss = model(experts, caption, prefix=config["prefix"])
+        optimizer.zero_grad()
+        accelerator.backward(loss)
+        if stock_adamw:
+            for p in model.parameters():                             # uninitialised "gradients" may hold NaN: keep the stock update finite
+                if p.grad is not None:
+                    p.grad.zero_()
+        optimizer.step()
+        steps += 1
+    assert steps == 2 and dry.calls["prismer_gemm_bf16"] > 200
+    frozen = [p for n, p in model.named_parameters() if "transformer.resblocks" in n and "adaptor" not in n]
+    assert frozen and all(not p.requires_grad and p.grad is None for p in frozen)        # freeze_vision (prismer.py:45-49)
+    model.eval()
+    with torch.no_grad():
+        captions = model(experts, train=False, prefix=config["prefix"])
+    assert isinstance(captions, list) and len(captions) == 2 and all(isinstance(c, str) for c in captions)
