@@ -184,3 +184,53 @@ def test_reference_training_loop_host_code(dry, monkeypatch, compact, stock_adam
     with torch.no_grad():
         captions = model(experts, train=False, prefix=config["prefix"])
     assert isinstance(captions, list) and len(captions) == 2 and all(isinstance(c, str) for c in captions)
+
+
+class _FakeStream:
+    def __init__(self, *a, **k): pass
+    def wait_stream(self, other): pass
+    def wait_event(self, e): pass
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
+
+
+class _FakeGraph:
+    replays = 0
+    def pool(self): return None
+    def replay(self): _FakeGraph.replays += 1
+
+
+@pytest.fixture()
+def fake_cuda(monkeypatch):
+    """Just enough of torch.cuda for GraphedTrainStep's control flow (streams, graph capture / replay) on a CPU-only host."""
+    import contextlib
+    monkeypatch.setattr(torch.cuda, "Stream", _FakeStream)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _FakeStream())
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", _FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", lambda g, pool=None: contextlib.nullcontext())
+    _FakeGraph.replays = 0
+
+
+@pytest.mark.parametrize("overlap,compact", [(False, False), (True, False), (True, True)])
+def test_graphed_train_step_host_code(dry, fake_cuda, overlap, compact):
+    from prismer_b200.optim import FusedAdamW
+    m = _tiny(True)
+    st = engine._store(m)
+    opt = FusedAdamW(m, lr=1e-3)
+    ex, ids, mask, labels = _batch(compact)
+    graphed = engine.GraphedTrainStep(m, ex, ids, mask, labels, overlap=overlap)
+    ex2, ids2, mask2, labels2 = _batch(compact)
+    graphed.load_inputs(ex2, ids2, mask2, labels2)                   # new batch into the static buffers (host or device tensors)
+    handles = []
+    comm = lambda t: (handles.append(t.numel()), type("H", (), {"wait": lambda self: None})())[1]
+    loss = graphed(comm)
+    assert loss is graphed.loss and _FakeGraph.replays == (2 if overlap else 1)
+    assert handles == ([st.n_train_dec, st.grad_t.numel() - st.n_train_dec] if overlap else [st.grad_t.numel()])
+    if overlap:                                                      # optimizer update of the decoder slice during the encoder backward
+        n0 = dry.calls.get("prismer_adamw_step", 0)
+        graphed(comm, on_decoder_grads=lambda: opt.step_range(0, st.n_train_dec, True, False))
+        opt.step_range(st.n_train_dec, st.n_train, False, True)
+        assert dry.calls["prismer_adamw_step"] == n0 + 2 and opt.t == 1
+    assert all(p.grad is not None for p in m.parameters() if p.requires_grad)       # published views of the flat buffer
