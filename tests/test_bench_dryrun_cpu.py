@@ -12,7 +12,7 @@ KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "
         "config", "e2e", "gpu_launches", "clocks"}
 
 
-@pytest.mark.parametrize("mode", [["train"], ["caption"], ["train", "compact", "overlap"]], ids=lambda m: "+".join(m))
+@pytest.mark.parametrize("mode", [["train"], ["caption", "compact"], ["train", "compact", "overlap"]], ids=lambda m: "+".join(m))
 def test_bench_host_logic(mode):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_dryrun.py")] + mode, cwd=ROOT, capture_output=True, text=True,
                        timeout=600)
