@@ -234,3 +234,22 @@ def test_graphed_train_step_host_code(dry, fake_cuda, overlap, compact):
         opt.step_range(st.n_train_dec, st.n_train, False, True)
         assert dry.calls["prismer_adamw_step"] == n0 + 2 and opt.t == 1
     assert all(p.grad is not None for p in m.parameters() if p.requires_grad)       # published views of the flat buffer
+
+
+@pytest.mark.parametrize("patch,res,experts", [(14, 56, EXPERTS), (16, 64, []), (14, 56, ["normal", "edge", "ocr_detection"])])
+def test_other_encoder_configurations_host_code(dry, patch, res, experts):
+    """Patch-14 models (experts resampled 64 -> 73 / 64 -> 18, positional embedding resized for the expert tokens) and PrismerZ
+    (rgb only: no stems, no resampler)."""
+    m, _ = build_model(256, 2, patch, res, experts, TINY_DEC, seed=3, device="cpu")
+    engine.prepare(m, torch.device("cpu"))
+    m.train()
+    ex = synthetic.synth_experts(2, res, experts, 64, 5)
+    ids, mask = synthetic.synth_tokens(2, 8, TINY_DEC["vocab_size"], 5, ragged=True)
+    labels = ids.masked_fill(ids == 1, -100)
+    random.seed(0)
+    engine.train_loss(m, ex, ids, mask, labels).backward()
+    assert ("prismer_resample_bilinear" in dry.calls) == (len(experts) > 0)
+    with torch.no_grad():
+        enc = m.expert_encoder(ex)
+    n_lat = 64 if experts else 0
+    assert enc.shape == ((res // patch) ** 2 + n_lat, 2, 256)
