@@ -35,6 +35,7 @@ def _req_cuda(*ts):
 
 
 GEMM_2CTA = os.environ.get("PRISMER_GEMM_2CTA") == "1"     # EXPERIMENTAL, default off (see gemm())
+GEMM_BN192 = os.environ.get("PRISMER_GEMM_BN192") == "1"   # EXPERIMENTAL, default off: 128 x 192 tiles for N = 768
 
 
 def _ld(t: torch.Tensor) -> int:
@@ -94,6 +95,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
         args.seed = seed.data_ptr()
     args.rng_stream = rng_stream
     args.force_bn, args.max_ctas, args.force_splits = force_bn, max_ctas, force_splits
+    if GEMM_BN192 and force_bn == 0 and N % 192 == 0 and N % 256 != 0 and M >= 2048 and not accumulate:
+        args.force_bn = 192          # EXPERIMENTAL: N = 768 as 4 x 192 columns (fuller last wave than 3 x 256)
     if two_cta is None:
         two_cta = GEMM_2CTA and M >= 2048 and N >= 256 and not accumulate and force_splits <= 1
     fn = _C.lib().prismer_gemm_bf16_2cta if two_cta else _C.lib().prismer_gemm_bf16

@@ -120,3 +120,18 @@ def test_gemm_attention_backward_cross_shapes(B, H, Lq, Lk, d):
     engine._gemm_attn_bwd(do, o, qb, kvb[:, :D], kvb[:, D:], lse, dq2, dkv2[:, :D], dkv2[:, D:], B, H, Lq, Lk)
     torch.cuda.synchronize()
     assert _rel(dq2, dq1) < 2e-2 and _rel(dkv2, dkv1) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K,tb", [(8320, 768, 768, False), (8320, 768, 3072, True), (2080, 768, 2304, False), (300, 200, 136, False)])
+def test_gemm_bn192_tile_matches_default(M, N, K, tb):
+    """128 x 192 tile instantiation of the validated GEMM template (force_bn = 192) against the default tile choice."""
+    from prismer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn((K, N) if tb else (N, K), device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    want = ops.gemm(a, b, trans_b=tb, bias=bias, act="quickgelu", residual=res)
+    got = ops.gemm(a, b, trans_b=tb, bias=bias, act="quickgelu", residual=res, force_bn=192)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)

@@ -31,7 +31,8 @@ for M, N, K in SHAPES:
     t1 = timed(lambda: ops.gemm(a, b, two_cta=False))
     t2 = timed(lambda: ops.gemm(a, b, two_cta=True))
     t2b = timed(lambda: ops.gemm(a, b, two_cta=True, force_bn=128))
+    t192 = timed(lambda: ops.gemm(a, b, two_cta=False, force_bn=192)) if N % 192 == 0 else float("nan")
     tc = timed(lambda: torch.matmul(a, b.t()))
     fl = 2.0 * M * N * K / 1e6
-    print(f"M{M:6d} N{N:5d} K{K:5d}: 1-CTA {t1:7.1f} us ({fl / t1:6.0f} TF/s) | 2-CTA {t2:7.1f} us ({fl / t2:6.0f}) bn128 {t2b:7.1f} us | "
+    print(f"M{M:6d} N{N:5d} K{K:5d}: 1-CTA {t1:7.1f} us ({fl / t1:6.0f} TF/s) | 2-CTA {t2:7.1f} us ({fl / t2:6.0f}) bn128 {t2b:7.1f} us | 1-CTA bn192 {t192:7.1f} us | "
           f"cuBLAS {tc:7.1f} us ({fl / tc:6.0f}) | identical {ok}")
