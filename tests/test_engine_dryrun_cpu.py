@@ -253,3 +253,25 @@ def test_other_encoder_configurations_host_code(dry, patch, res, experts):
         enc = m.expert_encoder(ex)
     n_lat = 64 if experts else 0
     assert enc.shape == ((res // patch) ** 2 + n_lat, 2, 256)
+
+
+def test_vqa_training_and_inference_host_code(dry):
+    """train_vqa.py:125 / :161 call shapes through the real engine host code: weighted loss, rank over a candidate list, beam generate."""
+    from prismer_b200.prismer_vqa import PrismerVQA
+    tiny = {"roberta_model": dict(TINY_DEC, model_name="roberta-tiny"), "vit_model": "tiny", "vit_dims": [16, 256, 2]}
+    m = PrismerVQA({"experts": EXPERTS, "prismer_model": "tiny", "image_resolution": 64, "freeze": "freeze_lang_vision", "prismer_config": tiny})
+    engine.prepare(m, torch.device("cpu"))
+    ex = synthetic.synth_experts(2, 64, EXPERTS, 64, 5)
+    qs, ans = ["what is on the table", "how many dogs are there in the picture"], ["a cup", "two"]
+    m.train()
+    random.seed(0)
+    loss = m(ex, qs, ans, weights=torch.tensor([1.0, 0.5]))
+    loss.backward()
+    named = dict(m.named_parameters())
+    assert named["text_decoder.roberta.encoder.layer.0.1.self.query.weight"].grad is not None        # cross-attention stays trainable
+    assert named["text_decoder.roberta.encoder.layer.0.0.attention.self.query.weight"].grad is None  # freeze_lang_vision (prismer.py:50-56)
+    m.eval()
+    with torch.no_grad():
+        r = m(ex, qs, ["a cup", "two", "pizza", "a red ball", "none"], train=False, inference="rank", k_test=3)
+        g = m(ex, qs, train=False, inference="generate")
+    assert r.shape == (2,) and len(g) == 2 and all(isinstance(s, str) for s in g)
