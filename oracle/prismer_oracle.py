@@ -340,17 +340,21 @@ def caption_train_loss(experts, input_ids, attention_mask, prompt_length, sd, pa
     return loss.mean(), logits, enc
 
 
-def greedy_generate(enc, input_ids, sd, heads, max_length=20, min_length=8, eos=2, pad=1):
-    """HF greedy search as driven by prismer_caption.py:45-50 with num_beams=1 and the
+def greedy_generate(enc, input_ids, sd, heads, max_length=20, min_length=8, eos=2, pad=1, attention_mask=None):
+    """HF greedy search as driven by prismer_caption.py:45-50 / prismer_vqa.py:51-57 with num_beams=1 and the
     no-cache ``prepare_inputs_for_generation`` (roberta.py:401-406): every step re-runs the
     decoder on the full prefix; logits[:, -1] -> MinLength processor (eos=-inf while
-    cur_len < min_length) -> argmax; finished rows emit pad; stop at max_length."""
+    cur_len < min_length) -> argmax; finished rows emit pad; stop at max_length.
+    ``attention_mask``: the prompt's mask (right-padded VQA questions, prismer_vqa.py:46-47); HF extends it with ones for
+    every generated token, and ``logits[:, -1]`` of a short row is the logits of its last PAD position.
+    Pinned against the unmodified reference by tests/golden/prismer_tiny_greedy.npz (oracle/gen_golden_greedy.py)."""
     ids = input_ids.clone()
+    mask = torch.ones_like(ids) if attention_mask is None else attention_mask.clone().to(ids.dtype)
     B = ids.shape[0]
     unfinished = torch.ones(B, dtype=torch.long)
     step_logits = []
     while ids.shape[1] < max_length:
-        logits, _ = decoder_forward(ids, torch.ones_like(ids), enc, sd, heads)
+        logits, _ = decoder_forward(ids, mask, enc, sd, heads)
         nxt = logits[:, -1].float().clone()
         if ids.shape[1] < min_length:
             nxt[:, eos] = -float("inf")
@@ -358,6 +362,7 @@ def greedy_generate(enc, input_ids, sd, heads, max_length=20, min_length=8, eos=
         tok = nxt.argmax(dim=-1)
         tok = tok * unfinished + pad * (1 - unfinished)
         ids = torch.cat([ids, tok[:, None]], dim=1)
+        mask = torch.cat([mask, torch.ones_like(mask[:, :1])], dim=1)
         unfinished = unfinished * (tok != eos).long()
         if unfinished.max() == 0:
             break

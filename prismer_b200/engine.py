@@ -137,23 +137,31 @@ class ParamStore:
         self.refresh(force=True)
 
     # -- bf16 compute copies ------------------------------------------------------------------------------------------
+    def _ver(self, trainable: bool) -> int:
+        """Change stamp of one half of the store.  In-place updates reach the masters two ways: through the flat buffers
+        (``dist.broadcast(st.master_t)``, the fused optimizer) and through the ``nn.Parameter`` views (a stock ``torch.optim``
+        step, ``load_state_dict``).  ``p.data = master[...]`` gave every Parameter its OWN version counter, so both are summed."""
+        flat, ps = (self.master_t, self.train_params) if trainable else (self.master_f, self.frozen_params)
+        return flat._version + sum(p._version for p in ps)
+
     def refresh(self, force: bool = False):
         """Re-derive the bf16 compute copies when the fp32 masters changed (optimizer step, load_state_dict)."""
         changed = False
-        if force or self.master_f._version != self._v_f:
+        vf, vt = self._ver(False), self._ver(True)
+        if force or vf != self._v_f:
             ops.cast_bf16(self.master_f, self.c16_f)
-            self._v_f = self.master_f._version
+            self._v_f = vf
             changed = True
-        if force or self.master_t._version != self._v_t:
+        if force or vt != self._v_t:
             ops.cast_bf16(self.master_t, self.c16_t)
-            self._v_t = self.master_t._version
+            self._v_t = vt
             changed = True
         if changed:
             self._repack_convs()
 
     def mark_fresh(self):
         """Called by the fused optimizer, which writes the bf16 copies itself."""
-        self._v_t = self.master_t._version
+        self._v_t = self._ver(True)
         self._repack_convs(trainable_only=True)
 
     def _repack_convs(self, trainable_only: bool = False):

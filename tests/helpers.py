@@ -69,6 +69,20 @@ BEAM_CASES = [
 ]
 
 
+# greedy decoding of right-padded (VQA-style) and uniform (caption-style) prompts: oracle/gen_golden_greedy.py
+GREEDY_CASES = [
+    dict(name="g_vqa_a", B=4, T0=7, ragged=True, S=20, boost=2.0, max_add=10, min_add=2),
+    dict(name="g_vqa_b", B=3, T0=6, ragged=True, S=12, boost=3.5, max_add=10, min_add=2),
+    dict(name="g_vqa_c", B=4, T0=8, ragged=True, S=12, boost=0.0, max_add=6, min_add=6),
+    dict(name="g_cap_a", B=4, T0=4, ragged=False, S=20, boost=3.0, max_add=16, min_add=4),
+]
+
+
+def load_greedy_golden():
+    z = np.load(os.path.join(GOLD, "prismer_tiny_greedy.npz"))
+    return {k: z[k] for k in z.files}
+
+
 def beam_decoder_state(template, boost):
     """Decoder state_dict (keys without the ``text_decoder.`` prefix) for a beam case: seeded fill + eos-bias boost."""
     sd = synthetic.synth_state_dict({"text_decoder." + k: v for k, v in template.items()}, BEAM_SEED)

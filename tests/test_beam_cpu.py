@@ -96,3 +96,51 @@ def test_beam_search_driver_plumbing_with_a_stand_in_engine(template, gold, monk
     assert calls["kv"] == 1 and calls["fwd"] >= 2
     assert np.array_equal(out.numpy(), gold[c["name"] + ".ids"])
     np.testing.assert_allclose(sc.numpy(), gold[c["name"] + ".scores"], rtol=2e-6, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------- greedy, right-padded prompts
+from tests.helpers import GREEDY_CASES, load_greedy_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("c", GREEDY_CASES, ids=[c["name"] for c in GREEDY_CASES])
+def test_oracle_greedy_matches_reference_on_padded_prompts(c, template):
+    """HF greedy of the unmodified reference decoder (oracle/gen_golden_greedy.py) vs the oracle restatement: ids bit-exact, incl.
+    rows whose prompt is right-padded (first generated token comes from the PAD position's logits)."""
+    gold = load_greedy_golden()
+    sd = beam_decoder_state(template, c["boost"])
+    ids, mask, enc = beam_case_inputs(c)
+    assert np.array_equal(ids.numpy(), gold[c["name"] + ".prompt"]) and np.array_equal(mask.numpy(), gold[c["name"] + ".mask"])
+    with torch.no_grad():
+        out, _ = O.greedy_generate(enc, ids, sd, HEADS, c["T0"] + c["max_add"], c["T0"] + c["min_add"], attention_mask=mask)
+    assert np.array_equal(out.numpy(), gold[c["name"] + ".ids"])
+
+
+@pytest.mark.parametrize("c", GREEDY_CASES, ids=[c["name"] for c in GREEDY_CASES])
+def test_product_greedy_loop_matches_reference_with_a_stand_in_engine(c, template, monkeypatch):
+    """``generation.greedy`` (prompt mask extended with ones, MinLength, pad after eos, early exit) with the engine's entry points
+    replaced by oracle-backed stand-ins on CPU tensors: the same ids as the reference's HF greedy."""
+    from types import SimpleNamespace
+    from prismer_b200 import engine, ops
+    gold = load_greedy_golden()
+    sd = beam_decoder_state(template, c["boost"])
+    ids, mask, enc = beam_case_inputs(c)
+
+    def fake_decoder_forward(dec, input_ids, attention_mask, enc_b, labels, weights, save, kv=None, last_only=False, **_):
+        assert last_only and not save
+        logits, _ = O.decoder_forward(input_ids, attention_mask, kv.enc.float(), sd, HEADS)
+        return logits[:, -1].float(), None, None, None
+
+    def fake_argmax(logits, V, suppress_eos=False, eos=2):
+        l = logits[:, :V].clone()
+        if suppress_eos:
+            l[:, eos] = -float("inf")
+        return l.argmax(dim=-1)
+
+    monkeypatch.setattr(engine, "cross_kv", lambda dec, e: SimpleNamespace(B=e.shape[0], enc=e))
+    monkeypatch.setattr(engine, "decoder_forward", fake_decoder_forward)
+    monkeypatch.setattr(engine, "_store", lambda m: SimpleNamespace(refresh=lambda: None))
+    monkeypatch.setattr(ops, "argmax", fake_argmax)
+    dec = SimpleNamespace(config=SimpleNamespace(eos_token_id=TINY_DEC["eos_token_id"], pad_token_id=TINY_DEC["pad_token_id"],
+                                                 vocab_size=TINY_DEC["vocab_size"]))
+    out = generation.greedy(dec, ids, enc, mask, max_length=c["T0"] + c["max_add"], min_length=c["T0"] + c["min_add"])
+    assert np.array_equal(out.numpy(), gold[c["name"] + ".ids"])

@@ -275,3 +275,28 @@ def test_vqa_training_and_inference_host_code(dry):
         r = m(ex, qs, ["a cup", "two", "pizza", "a red ball", "none"], train=False, inference="rank", k_test=3)
         g = m(ex, qs, train=False, inference="generate")
     assert r.shape == (2,) and len(g) == 2 and all(isinstance(s, str) for s in g)
+
+
+def test_refresh_sees_updates_made_through_the_parameters(dry):
+    """a stock torch optimizer / load_state_dict write the masters through the nn.Parameter views, whose version
+    counters are not the flat buffers' -- refresh() must re-cast the bf16 compute copies after either, and must not when idle."""
+    m = _tiny(True)
+    st = m._prismer_store
+    st.refresh()
+    n0 = dry.calls.get("prismer_cast_f32_bf16", 0)
+    st.refresh()
+    assert dry.calls.get("prismer_cast_f32_bf16", 0) == n0                      # nothing changed -> no cast
+    p = m.text_decoder.lm_head.dense.weight
+    p.grad = torch.ones_like(p)
+    torch.optim.AdamW([p], lr=1e-2).step()
+    st.refresh()
+    n1 = dry.calls.get("prismer_cast_f32_bf16", 0)
+    assert n1 > n0, "stock optimizer step not detected"
+    m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    st.refresh()
+    assert dry.calls.get("prismer_cast_f32_bf16", 0) > n1, "load_state_dict on a prepared model not detected"
+    n2 = dry.calls.get("prismer_cast_f32_bf16", 0)
+    with torch.no_grad():
+        st.master_t.mul_(1.0)                                                      # flat-buffer writes (broadcast, fused optimizer) still count
+    st.refresh()
+    assert dry.calls.get("prismer_cast_f32_bf16", 0) > n2

@@ -8,8 +8,7 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-# Written after this round's GPU budget was spent: non-strict xfail until looked at on hardware ("X" = passed).
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending")]
+pytestmark = pytest.mark.gpu
 
 
 def test_c_abi_example_builds_and_runs(tmp_path):

@@ -16,10 +16,7 @@ import torch
 from prismer_b200 import data, synthetic
 from tests.helpers import GOLD, build_model, label_case
 
-# Written after this round's GPU budget was spent: the first hardware run is the driver's round-end run.  Non-strict xfail so a
-# defect HERE shows up as "x" without masking the hardware-validated suite that runs before it ("X" = passed); the marker is
-# removed once a B200 run has been looked at.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending")]
+pytestmark = pytest.mark.gpu
 
 
 def test_expand_labels_matches_reference_post_label_process():
