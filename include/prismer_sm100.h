@@ -127,6 +127,10 @@ typedef struct PrismerAttnArgs {
 
 int prismer_attention_fwd(const PrismerAttnArgs* args, cudaStream_t stream);
 int prismer_attention_bwd(const PrismerAttnArgs* args, cudaStream_t stream);
+/* Kernel selection for the two calls above.  0 (default): head dim 64, no mask / dropout, 64 <= Lq <= 320, Lk <= 320 (the ViT blocks'
+ * nn.MultiheadAttention core, vit.py:52-53) run on the tcgen05 / TMEM kernels (csrc/attention_sm100.cu); every other shape on the
+ * mma.sync kernels (csrc/attention.cu).  1: always the mma.sync kernels (A/B tests of the two implementations). */
+int prismer_set_attention_path(int mode);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Elementwise / reduction helpers (HBM-bound).
@@ -247,15 +251,6 @@ typedef struct PrismerBatchedGemmArgs {
   int force_bn;   /* 0 = pick the N tile (64 / 128 / 256) that pads N least; tuning override otherwise */
 } PrismerBatchedGemmArgs;
 int prismer_gemm_bf16_batched(const PrismerBatchedGemmArgs* args, cudaStream_t stream);
-/* EXPERIMENTAL: register-lean prismer_layernorm_bwd (inputs kept packed, dgamma/dbeta accumulated in shared memory or skipped when
- * NULL): 2-3 resident blocks per SM instead of 1.  Same signature and arithmetic; D <= 1024.  csrc/layernorm_v2.cu. */
-int prismer_layernorm_bwd_v2(const void* dy, long long lddy, const void* x, long long ldx, const float* mean, const float* rstd,
-                             const float* gamma, const void* dres, long long lddres, void* dx, long long lddx, void* dz,
-                             long long lddz, float* dgamma, float* dbeta, int rows, int D, float drop_p,
-                             const unsigned long long* seed, uint32_t rng_stream, cudaStream_t stream);
-/* EXPERIMENTAL: prismer_gemm_bf16 on CTA pairs (tcgen05.mma.cta_group::2, 256 x BN tile per pair, each CTA loading its half of
- * both operands); same argument block, no split-K, max_ctas counts pairs.  csrc/gemm2_sm100.cu. */
-int prismer_gemm_bf16_2cta(const PrismerGemmArgs* args, cudaStream_t stream);
 /* in place row softmax of bf16 scores [rows, ld] over the first Lk columns (padding columns are zeroed). */
 int prismer_softmax_rows(void* s, long long rows, int Lk, int ld, cudaStream_t stream);
 /* delta[(b*H+h)*Lq + q] = sum_d dO*O, tensors addressed as base + b*bs + q*rs + h*d. */

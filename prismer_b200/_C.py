@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, Structure, c_float, c_int, c_longlong, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprismer_sm100.so")
+# PRISMER_LIB selects another in-tree BUILD of the same library (e.g. the -DPRISMER_PDL variant); there is still no fallback
+LIB_PATH = os.environ.get("PRISMER_LIB") or os.path.join(_HERE, "libprismer_sm100.so")
 
 ERRORS = {-1: "bad shape / argument", -2: "misaligned pointer or leading dimension", -3: "unsupported architecture (needs sm_100)",
           -4: "CUDA runtime error", -5: "CUDA driver entry point (cuTensorMapEncodeTiled) unavailable"}
@@ -100,8 +101,6 @@ def _declare(L):
     L.prismer_check_device.restype = c_int
     L.prismer_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
     L.prismer_gemm_bf16.restype = c_int
-    L.prismer_gemm_bf16_2cta.argtypes = [POINTER(GemmArgs), c_void_p]
-    L.prismer_gemm_bf16_2cta.restype = c_int
     L.prismer_gemm_bf16_batched.argtypes = [POINTER(BatchedGemmArgs), c_void_p]
     L.prismer_gemm_bf16_batched.restype = c_int
     for fn in ("prismer_attention_fwd", "prismer_attention_bwd"):

@@ -6,7 +6,6 @@ P, I, L, F, U32, U64 = c_void_p, c_int, c_longlong, c_float, c_uint32, c_ulonglo
 SIGNATURES = {
     "prismer_layernorm_fwd": [P, L, P, P, P, L, P, P, I, I, F, P],
     "prismer_layernorm_bwd": [P, L, P, L, P, P, P, P, L, P, L, P, L, P, P, I, I, F, P, U32, P],
-    "prismer_layernorm_bwd_v2": [P, L, P, L, P, P, P, P, L, P, L, P, L, P, P, I, I, F, P, U32, P],
     "prismer_colsum": [P, L, P, I, I, P],
     "prismer_act_bwd": [P, P, P, L, I, P],
     "prismer_cast_f32_bf16": [P, P, L, P],
@@ -39,6 +38,7 @@ SIGNATURES = {
     "prismer_unpad_add": [P, P, L, I, I, P],
     "prismer_softmax_rows": [P, L, I, I, P],
     "prismer_attn_delta": [P, P, L, L, P, I, I, I, I, P],
+    "prismer_set_attention_path": [I],
 }
 
 

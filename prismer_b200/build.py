@@ -11,12 +11,13 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-LIB = os.path.join(HERE, "libprismer_sm100.so")
-OBJ_DIR = os.path.join(HERE, "build")
+PDL = os.environ.get("PRISMER_PDL") == "1"      # opt-in variant: programmatic dependent launch for the hot kernels (common.cuh)
+LIB = os.path.join(HERE, "libprismer_sm100_pdl.so" if PDL else "libprismer_sm100.so")
+OBJ_DIR = os.path.join(HERE, "build_pdl" if PDL else "build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]
-if os.environ.get("PRISMER_PDL") == "1":      # opt-in experiment: programmatic dependent launch for the hot kernels (common.cuh)
+if PDL:
     NVCC_FLAGS.append("-DPRISMER_PDL")
 
 

@@ -795,10 +795,15 @@ int fill(AttnParams& p, const PrismerAttnArgs* a) {
 
 }  // namespace
 
+// tcgen05 / TMEM kernels for the encoder's self-attention shapes (attention_sm100.cu): 1 = handled, 0 = shape not covered
+int attn_sm100_try_fwd(const PrismerAttnArgs* a, cudaStream_t stream, int* rc_out);
+int attn_sm100_try_bwd(const PrismerAttnArgs* a, cudaStream_t stream, int* rc_out);
+
 extern "C" int prismer_attention_fwd(const PrismerAttnArgs* a, cudaStream_t stream) {
   AttnParams p;
   int rc = fill(p, a);
   if (rc) return rc;
+  if (attn_sm100_try_fwd(a, stream, &rc)) return rc;
   dim3 grid((p.Lq + TQ - 1) / TQ, p.H, p.B);
 #define FWD(D_)                                                                     \
   { rc = set_smem(attn_fwd_kernel<D_>, smem_fwd<D_>()); if (rc) return rc;          \
@@ -815,6 +820,7 @@ extern "C" int prismer_attention_bwd(const PrismerAttnArgs* a, cudaStream_t stre
   if (!p.dout || !p.dq || !p.dk || !p.dv || !p.delta || !p.lse) return PRISMER_ERR_SHAPE;
   const long long strides[] = {a->do_bs, a->do_rs, a->dq_bs, a->dq_rs, a->dk_bs, a->dk_rs, a->dv_bs, a->dv_rs};
   for (long long s : strides) if (s % 8) return PRISMER_ERR_ALIGN;
+  if (attn_sm100_try_bwd(a, stream, &rc)) return rc;
   if (p.Lq <= TQ) {   // all queries in one tile: fused single-kernel backward
     dim3 gf(1, p.H, p.B);
 #define BWDF(D_)                                                                                 \

@@ -26,8 +26,8 @@ template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int kTmemCols = (BN == 192) ? 512 : 2 * BN;  // two accumulator stages; the allocation must be a power of two >= 32
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages; the allocation must be a power of two >= 32
   static constexpr int kStagingBytes = kNumEpiWarps * 4096;   // per-epilogue-warp 32x32 staging tile (coalesced stores)
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStagingBytes;
 };
@@ -456,8 +456,7 @@ extern "C" int prismer_gemm_bf16(const PrismerGemmArgs* a, cudaStream_t stream) 
     const int kps = (num_k + a->force_splits - 1) / a->force_splits;
     splits = (num_k + kps - 1) / kps;
   }
-  // BN = 192 (N = 768 = 4 x 192: 260 tiles = 1.76 waves at M = 8320 instead of 195 = 1.32) is an explicit experiment: force_bn only
-  if (bn != 64 && bn != 128 && bn != 192 && bn != 256) return PRISMER_ERR_SHAPE;
+  if (bn != 64 && bn != 128 && bn != 256) return PRISMER_ERR_SHAPE;
 
   CUtensorMap ta, tb;
   int rc;
@@ -491,7 +490,6 @@ extern "C" int prismer_gemm_bf16(const PrismerGemmArgs* a, cudaStream_t stream) 
   if (a->transA && !a->transB) return launch<BN_, true, false>(ta, tb, a->M, a->N, a->K, splits, ep, sms, stream);   \
   return launch<BN_, true, true>(ta, tb, a->M, a->N, a->K, splits, ep, sms, stream);
   if (bn == 256) { DISPATCH(256) }
-  if (bn == 192) { DISPATCH(192) }
   if (bn == 128) { DISPATCH(128) }
   DISPATCH(64)
 #undef DISPATCH

@@ -193,6 +193,12 @@ extern "C" int prismer_layernorm_fwd(const void* x, long long ldx, const float* 
   return LAUNCH_CHECK();
 }
 
+// register-lean kernel for D <= 1024 (layernorm_v2.cu)
+int prismer_ln_bwd_lean(const void* dy, long long lddy, const void* x, long long ldx, const float* mean, const float* rstd,
+                        const float* gamma, const void* dres, long long lddres, void* dx, long long lddx, void* dz, long long lddz,
+                        float* dgamma, float* dbeta, int rows, int D, float drop_p, const unsigned long long* seed, uint32_t rng_stream,
+                        cudaStream_t stream);
+
 extern "C" int prismer_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* mean,
                                      const float* rstd, const float* gamma, const void* dres, long long lddres, void* dx,
                                      long long lddx, void* dz, long long lddz, float* dgamma, float* dbeta, int rows,
@@ -202,6 +208,9 @@ extern "C" int prismer_layernorm_bwd(const void* dy, long long lddy, const void*
   if (D <= 0 || (D % 8) || D > 2048 || (ldx % 8) || (lddy % 8) || (lddx % 8)) return PRISMER_ERR_SHAPE;
   if ((dgamma == nullptr) != (dbeta == nullptr)) return PRISMER_ERR_SHAPE;
   if (dz && drop_p > 0.f && !seed) return PRISMER_ERR_SHAPE;
+  if (D <= 1024)
+    return prismer_ln_bwd_lean(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dz, lddz, dgamma, dbeta, rows, D, drop_p, seed,
+                               rng_stream, stream);
   const int vpl = (D / 8 + 31) / 32;
   int grid = grid_for(rows);
   if (dgamma && grid > 148 * 4) grid = 148 * 4;  // fewer, fatter blocks -> fewer atomics

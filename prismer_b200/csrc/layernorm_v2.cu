@@ -1,12 +1,13 @@
-// EXPERIMENTAL (round-2 candidate; exported as prismer_layernorm_bwd_v2, NOT on the default path, not yet run on hardware):
-// register-lean LayerNorm backward.  The validated ln_bwd_kernel<3> (D = 768) needs 146 registers -> ONE 256-thread block per SM
-// (8 warps) and ~1 TB/s (profiles/launches_r1.csv: 38 MB in 37 us), because every lane carries 48 dgamma/dbeta accumulators plus the
+// Register-lean LayerNorm backward: the kernel behind prismer_layernorm_bwd for D <= 1024 (every LayerNorm of Prismer-BASE / LARGE).
+// Validated on B200 in round 2 against the round-1 kernel of layernorm.cu (dx / dz equal up to one bf16 ulp, dgamma / dbeta up to fp32
+// summation order) and adopted: 102 calls of a BASE step 2.81 ms -> 1.89 ms.  The round-1 ln_bwd_kernel<3> (D = 768) needs 146
+// registers -> ONE 256-thread block per SM (8 warps) and ~1 TB/s, because every lane carries 48 dgamma/dbeta accumulators plus the
 // 48 unpacked xhat / g*dy values across the row reduction.  Here
 //   * the inputs stay PACKED in registers (x and dy as uint4: 2 x VPL registers x 4) and are unpacked again for the output pass,
 //   * dgamma / dbeta are accumulated in each warp's private shared-memory slice (the [warps][2][D] buffer the validated kernel
 //     already allocates for its final reduction) with conflict-free 128-bit read-modify-writes -- and not at all when the
 //     LayerNorm is frozen (template flag), which is 24 of the 36 ViT sites under freeze_vision.
-// Same C signature and arithmetic as prismer_layernorm_bwd (dx / dz are bit-identical; dgamma / dbeta differ in summation order).
+// Same arguments and arithmetic as the round-1 kernel (which remains the path for 1024 < D <= 2048).
 #include "common.cuh"
 #include "prismer_sm100.h"
 
@@ -151,15 +152,11 @@ int launch_ln2(const void* dy, long long lddy, const void* x, long long ldx, con
 
 }  // namespace
 
-extern "C" int prismer_layernorm_bwd_v2(const void* dy, long long lddy, const void* x, long long ldx, const float* mean,
+int prismer_ln_bwd_lean(const void* dy, long long lddy, const void* x, long long ldx, const float* mean,
                                         const float* rstd, const float* gamma, const void* dres, long long lddres, void* dx,
                                         long long lddx, void* dz, long long lddz, float* dgamma, float* dbeta, int rows, int D,
                                         float drop_p, const unsigned long long* seed, uint32_t rng_stream, cudaStream_t stream) {
-  if (rows <= 0) return PRISMER_OK;
-  if (D <= 0 || (D % 8) || D > 1024 || (ldx % 8) || (lddy % 8) || (lddx % 8)) return PRISMER_ERR_SHAPE;
-  if ((dgamma == nullptr) != (dbeta == nullptr)) return PRISMER_ERR_SHAPE;
-  if (dz && drop_p > 0.f && !seed) return PRISMER_ERR_SHAPE;
-  const int vpl = (D / 8 + 31) / 32;
+  const int vpl = (D / 8 + 31) / 32;      // arguments validated by the caller (prismer_layernorm_bwd)
 #define LN2(V)                                                                                                                   \
   return dgamma ? launch_ln2<V, true>(dy, lddy, x, ldx, mean, rstd, gamma, dres, lddres, dx, lddx, dz, lddz, dgamma, dbeta, rows, D, \
                                       drop_p, seed, rng_stream, stream)                                                          \

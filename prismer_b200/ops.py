@@ -34,10 +34,6 @@ def _req_cuda(*ts):
             raise _C.PrismerError("prismer_b200 ops need CUDA tensors (there is no CPU fallback)")
 
 
-GEMM_2CTA = os.environ.get("PRISMER_GEMM_2CTA") == "1"     # EXPERIMENTAL, default off (see gemm())
-GEMM_BN192 = os.environ.get("PRISMER_GEMM_BN192") == "1"   # EXPERIMENTAL, default off: 128 x 192 tiles for N = 768
-
-
 def _ld(t: torch.Tensor) -> int:
     assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), f"need a 2-D row-major view, got {tuple(t.shape)} / {t.stride()}"
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
@@ -48,10 +44,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
          aux_out: Optional[torch.Tensor] = None, aux_in: Optional[torch.Tensor] = None, act_grad=0,
          out: Optional[torch.Tensor] = None, out_dtype=BF16, accumulate: bool = False, alpha: float = 1.0,
          drop_p: float = 0.0, seed: Optional[torch.Tensor] = None, rng_stream: int = 0, force_bn: int = 0,
-         max_ctas: int = 0, force_splits: int = 0, two_cta: Optional[bool] = None) -> torch.Tensor:
-    """C[M,N] = epilogue(alpha * op(A) . op(B)^T); A is [M,K] (or [K,M] if trans_a), B is [N,K] (or [K,N] if trans_b).
-    ``two_cta``: EXPERIMENTAL cta_group::2 kernel (csrc/gemm2_sm100.cu); None = only when PRISMER_GEMM_2CTA=1 and the shape is
-    encoder-sized (M >= 2048, N >= 256, no split-K candidate)."""
+         max_ctas: int = 0, force_splits: int = 0) -> torch.Tensor:
+    """C[M,N] = epilogue(alpha * op(A) . op(B)^T); A is [M,K] (or [K,M] if trans_a), B is [N,K] (or [K,N] if trans_b)."""
     _req_cuda(a, b)
     assert a.dtype == BF16 and b.dtype == BF16
     if trans_a:
@@ -95,11 +89,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, trans_a: bool = False, trans_b: bo
         args.seed = seed.data_ptr()
     args.rng_stream = rng_stream
     args.force_bn, args.max_ctas, args.force_splits = force_bn, max_ctas, force_splits
-    if GEMM_BN192 and force_bn == 0 and N % 192 == 0 and N % 256 != 0 and M >= 2048 and not accumulate:
-        args.force_bn = 192          # EXPERIMENTAL: N = 768 as 4 x 192 columns (fuller last wave than 3 x 256)
-    if two_cta is None:
-        two_cta = GEMM_2CTA and M >= 2048 and N >= 256 and not accumulate and force_splits <= 1
-    fn = _C.lib().prismer_gemm_bf16_2cta if two_cta else _C.lib().prismer_gemm_bf16
+    fn = _C.lib().prismer_gemm_bf16
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -128,19 +118,15 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return (y.view(x.shape) if out is None else y), mean, rstd
 
 
-LN_BWD_V2 = os.environ.get("PRISMER_LN_BWD_V2") == "1"       # EXPERIMENTAL register-lean backward (csrc/layernorm_v2.cu), default off
-
-
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, dres=None, dgamma=None, dbeta=None, need_dx=True, dz=False,
-                  drop_p: float = 0.0, seed=None, rng_stream: int = 0, v2=None):
+                  drop_p: float = 0.0, seed=None, rng_stream: int = 0):
     D = x.shape[-1]
     dy2, x2 = dy.reshape(-1, D), x.reshape(-1, D)
     rows = x2.shape[0]
     dx = torch.empty_like(x2) if need_dx else None
     dzt = torch.empty_like(x2) if dz else None
     dres2 = dres.reshape(-1, D) if dres is not None else None
-    fn = _C.lib().prismer_layernorm_bwd_v2 if (LN_BWD_V2 if v2 is None else v2) and D <= 1024 else _C.lib().prismer_layernorm_bwd
-    check(fn(dy2.data_ptr(), _ld(dy2), x2.data_ptr(), _ld(x2), mean.data_ptr(), rstd.data_ptr(),
+    check(_C.lib().prismer_layernorm_bwd(dy2.data_ptr(), _ld(dy2), x2.data_ptr(), _ld(x2), mean.data_ptr(), rstd.data_ptr(),
                                          gamma.data_ptr(), _p(dres2), _ld(dres2) if dres2 is not None else 0,
                                          _p(dx), _ld(dx) if dx is not None else 0, _p(dzt), _ld(dzt) if dzt is not None else 0,
                                          _p(dgamma), _p(dbeta), rows, D, drop_p, _p(seed), rng_stream, _stream()),
@@ -152,6 +138,11 @@ def _bhv(t: torch.Tensor, H: int, d: int):
     """[B, L, H*d]-shaped view (last dim contiguous) -> (ptr, batch stride, row stride)."""
     assert t.dim() == 3 and t.stride(2) == 1 and t.shape[2] == H * d and t.dtype == BF16, (t.shape, t.stride())
     return t.data_ptr(), t.stride(0), t.stride(1)
+
+
+def set_attention_path(legacy: bool):
+    """True: every attention call runs the mma.sync kernels; False (default): the tcgen05 / TMEM kernels where they apply."""
+    check(_C.lib().prismer_set_attention_path(int(bool(legacy))), "set_attention_path")
 
 
 def attention_fwd(q, k, v, heads: int, *, causal=False, key_mask=None, drop_p=0.0, seed=None, rng_stream=0,

@@ -40,6 +40,15 @@ CASES = [  # B, H, Lq, Lk, d, causal, masked
     (1, 8, 64, 1600, 128, False, False),   # LARGE resampler (d = 128)
     (2, 4, 8, 8, 64, True, True),
     (2, 4, 100, 100, 64, True, False),     # causal across tile boundary
+    # tcgen05 / TMEM path (csrc/attention_sm100.cu): d = 64, no mask / dropout, 64 <= Lq <= 320, Lk <= 320
+    (3, 12, 320, 320, 64, False, False),   # Prismer-LARGE @224: S = 256 + 64 (16 heads there; 3 full-ish tiles)
+    (2, 12, 196, 196, 64, False, False),   # PrismerZ (no latents)
+    (2, 16, 256, 256, 64, False, False),   # exactly two full tiles
+    (1, 4, 64, 64, 64, False, False),      # smallest shape routed to the tensor-memory kernels
+    (2, 3, 130, 130, 64, False, False),    # two-row tail tile
+    (2, 4, 100, 300, 64, False, False),    # Lq != Lk
+    (2, 4, 272, 17, 64, False, False),     # one-row key tail, three query tiles
+    (32, 12, 260, 260, 64, False, False),  # the Prismer-BASE training shape (384 CTAs on 148 SMs)
 ]
 
 
@@ -99,3 +108,34 @@ def test_attention_dropout_consistency():
     lhs = (do.float() * o.float()).sum().item()
     rhs = (dv.float() * v.float()).sum().item()
     assert abs(lhs - rhs) / max(abs(lhs), 1.0) < 2e-2, (lhs, rhs)
+
+
+@pytest.mark.parametrize("B,H,S", [(4, 12, 260), (2, 16, 320), (3, 12, 196)])
+def test_tensor_memory_kernels_match_mma_sync_kernels_on_the_engine_layout(B, H, S):
+    """The two implementations behind prismer_attention_fwd / _bwd (tcgen05 + TMEM, csrc/attention_sm100.cu; mma.sync,
+    csrc/attention.cu) on the layout the ViT blocks use: q / k / v are column slices of the seq-first packed projection
+    [S*B, 3D] (rows s*B + b), outputs are written through the same strides."""
+    from prismer_b200 import engine, ops
+    d, D = 64, 64 * H
+    g = torch.Generator(device="cuda").manual_seed(S + B)
+    qkv = torch.randn(S * B, 3 * D, device="cuda", generator=g).to(torch.bfloat16)
+    do = torch.randn(S * B, D, device="cuda", generator=g).to(torch.bfloat16)
+    q3 = engine._sf(qkv, S, B)
+    res = []
+    for legacy in (True, False):
+        ops.set_attention_path(legacy)
+        try:
+            o = torch.zeros(S * B, D, device="cuda", dtype=torch.bfloat16)
+            _, lse = ops.attention_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], H, out=engine._sf(o, S, B))
+            dqkv = torch.zeros_like(qkv)
+            d3 = engine._sf(dqkv, S, B)
+            ops.attention_bwd(engine._sf(do, S, B), q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], engine._sf(o, S, B), lse, H,
+                              dq=d3[..., :D], dk=d3[..., D:2 * D], dv=d3[..., 2 * D:])
+            torch.cuda.synchronize()
+        finally:
+            ops.set_attention_path(False)
+        res.append((o, lse, dqkv))
+    (o1, l1, g1), (o2, l2, g2) = res
+    assert _rel(o2.float(), o1.float()) < 4e-3 and _rel(l2, l1) < 1e-5
+    for c in range(3):
+        assert _rel(g2[:, c * D:(c + 1) * D].float(), g1[:, c * D:(c + 1) * D].float()) < 8e-3, c

@@ -13,7 +13,7 @@ from prismer_b200 import _C, _C_decl, engine, ops, synthetic
 from tests.helpers import TINY_DEC, build_model
 
 EXPERTS = synthetic.DEFAULT_EXPERTS
-STRUCT_CALLS = {"prismer_gemm_bf16": 2, "prismer_gemm_bf16_2cta": 2, "prismer_gemm_bf16_batched": 2, "prismer_attention_fwd": 2,
+STRUCT_CALLS = {"prismer_gemm_bf16": 2, "prismer_gemm_bf16_batched": 2, "prismer_attention_fwd": 2,
                 "prismer_attention_bwd": 2}
 
 
@@ -92,19 +92,6 @@ def test_experimental_attention_paths_host_code(dry, monkeypatch, mode):
     engine.train_loss(m, ex, ids, mask, labels).backward()
     # per ViT layer: bwd = P (only when recomputed) + dV + dS + dQ + dK; the resampler (d = 32 here) joins in "bwd" mode
     assert dry.calls["prismer_gemm_bf16_batched"] >= 2 * (4 + (2 if mode == "fwd+bwd" else 1)) and dry.calls["prismer_attn_delta"] >= 2
-
-
-def test_two_cta_and_ln_v2_switches_host_code(dry, monkeypatch):
-    monkeypatch.setattr(ops, "GEMM_2CTA", True)
-    monkeypatch.setattr(ops, "LN_BWD_V2", True)
-    m = _tiny(True)
-    ex, ids, mask, labels = _batch()
-    random.seed(0)
-    engine.train_loss(m, ex, ids, mask, labels).backward()
-    assert dry.calls.get("prismer_layernorm_bwd_v2", 0) > 10 and "prismer_layernorm_bwd" not in dry.calls
-    a = torch.empty(4096, 256, dtype=torch.bfloat16)
-    ops.gemm(a, torch.empty(512, 256, dtype=torch.bfloat16))
-    assert dry.calls.get("prismer_gemm_bf16_2cta", 0) == 1          # encoder-sized shape -> the pair kernel
 
 
 def test_generation_and_rank_host_code(dry):

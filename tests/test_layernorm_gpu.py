@@ -36,6 +36,22 @@ def test_layernorm_fwd_bwd(rows, D):
     assert _rel(dbeta, bf.grad) < 1e-4
 
 
+@pytest.mark.parametrize("rows,D", [(8320, 768), (77, 256), (1030, 1024)])
+def test_layernorm_bwd_frozen_gamma(rows, D):
+    """Frozen LayerNorm sites (24 of the 36 ViT sites under freeze_vision): no dgamma / dbeta, dx only (+ residual gradient)."""
+    from prismer_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(rows, D, device="cuda", generator=g).to(torch.bfloat16)
+    gamma = 1 + 0.1 * torch.randn(D, device="cuda", generator=g)
+    _, mean, rstd = ops.layernorm_fwd(x, gamma, torch.zeros(D, device="cuda"))
+    dy = torch.randn(rows, D, device="cuda", generator=g).to(torch.bfloat16)
+    xf = x.float().requires_grad_(True)
+    F.layer_norm(xf, (D,), gamma, None, 1e-5).backward(dy.float())
+    dx, dz = ops.layernorm_bwd(dy, x, mean, rstd, gamma)
+    torch.cuda.synchronize()
+    assert dz is None and _rel(dx.float(), xf.grad) < 4e-3
+
+
 def test_layernorm_bwd_dropout_matches_gemm_mask():
     """dz of the LN backward must use the very mask the forward GEMM epilogue applied (same seed/stream/element)."""
     from prismer_b200 import ops

@@ -26,7 +26,7 @@ class Rec:
     def __getattr__(self, name):
         def fn(*a):
             calls[name] += 1
-            if name in ("prismer_gemm_bf16", "prismer_gemm_bf16_2cta"):
+            if name == "prismer_gemm_bf16":
                 g = ctypes.cast(a[0], ctypes.POINTER(_C.GemmArgs)).contents
                 gemms.append((g.M, g.N, g.K, g.transA, g.transB, g.accumulate))
             elif name in ("prismer_attention_fwd", "prismer_attention_bwd"):
