@@ -115,6 +115,7 @@ __device__ __forceinline__ bool key_ok(const AttnParams& p, int b, int qi, int k
 template <int D>
 __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  PDL_GRID_SYNC();
   constexpr int TILE = 64 * (D + PAD);
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
   bf16* sKV = sQ + TILE;                        // [2 stages][K | V]
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
 template <int D>
 __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  PDL_GRID_SYNC();
   constexpr int TILE = 64 * (D + PAD);
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
   bf16* sdO = sQ + TILE;
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(AttnParams p) {
 template <int D>
 __global__ void __launch_bounds__(NWARP * 32, (D <= 64) ? 3 : 1) attn_bwd_dkv_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  PDL_GRID_SYNC();
   constexpr int TILE = 64 * (D + PAD);
   bf16* sK = reinterpret_cast<bf16*>(smem_raw);
   bf16* sV = sK + TILE;
@@ -564,6 +567,7 @@ __device__ __forceinline__ void frag_a_t(uint32_t (&a)[4], const bf16* s, int m0
 template <int D>
 __global__ void __launch_bounds__(NWARP * 32) attn_bwd_fused_kernel(AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  PDL_GRID_SYNC();
   constexpr int TILE = 64 * (D + PAD);
   constexpr int PLD = TK + PAD;
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
@@ -807,7 +811,7 @@ extern "C" int prismer_attention_fwd(const PrismerAttnArgs* a, cudaStream_t stre
   dim3 grid((p.Lq + TQ - 1) / TQ, p.H, p.B);
 #define FWD(D_)                                                                     \
   { rc = set_smem(attn_fwd_kernel<D_>, smem_fwd<D_>()); if (rc) return rc;          \
-    attn_fwd_kernel<D_><<<grid, NWARP * 32, smem_fwd<D_>(), stream>>>(p); }
+    pdl_launch(attn_fwd_kernel<D_>, grid, dim3(NWARP * 32), static_cast<size_t>(smem_fwd<D_>()), stream, p); }
   switch (a->d) { case 32: FWD(32) break; case 64: FWD(64) break; case 96: FWD(96) break; default: FWD(128) break; }
 #undef FWD
   return LAUNCH_CHECK();
@@ -825,7 +829,7 @@ extern "C" int prismer_attention_bwd(const PrismerAttnArgs* a, cudaStream_t stre
     dim3 gf(1, p.H, p.B);
 #define BWDF(D_)                                                                                 \
   { rc = set_smem(attn_bwd_fused_kernel<D_>, smem_fused<D_>()); if (rc) return rc;               \
-    attn_bwd_fused_kernel<D_><<<gf, NWARP * 32, smem_fused<D_>(), stream>>>(p); }
+    pdl_launch(attn_bwd_fused_kernel<D_>, gf, dim3(NWARP * 32), static_cast<size_t>(smem_fused<D_>()), stream, p); }
     switch (a->d) { case 32: BWDF(32) break; case 64: BWDF(64) break; case 96: BWDF(96) break; default: BWDF(128) break; }
 #undef BWDF
     return LAUNCH_CHECK();
@@ -834,8 +838,8 @@ extern "C" int prismer_attention_bwd(const PrismerAttnArgs* a, cudaStream_t stre
 #define BWD(D_)                                                                                  \
   { rc = set_smem(attn_bwd_dq_kernel<D_>, smem_dq<D_>()); if (rc) return rc;                     \
     rc = set_smem(attn_bwd_dkv_kernel<D_>, smem_dkv<D_>()); if (rc) return rc;                   \
-    attn_bwd_dq_kernel<D_><<<gq, NWARP * 32, smem_dq<D_>(), stream>>>(p);                        \
-    attn_bwd_dkv_kernel<D_><<<gk, NWARP * 32, smem_dkv<D_>(), stream>>>(p); }
+    pdl_launch(attn_bwd_dq_kernel<D_>, gq, dim3(NWARP * 32), static_cast<size_t>(smem_dq<D_>()), stream, p);                        \
+    pdl_launch(attn_bwd_dkv_kernel<D_>, gk, dim3(NWARP * 32), static_cast<size_t>(smem_dkv<D_>()), stream, p); }
   switch (a->d) { case 32: BWD(32) break; case 64: BWD(64) break; case 96: BWD(96) break; default: BWD(128) break; }
 #undef BWD
   return LAUNCH_CHECK();

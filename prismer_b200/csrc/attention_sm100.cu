@@ -25,7 +25,8 @@
 namespace {
 
 constexpr int kMaxL = 320;                 // rows of Q / K that fit the shared-memory and TMEM plan
-constexpr int kThreads = 192;              // warp 0: TMA, warp 1: MMA issue + TMEM owner, warps 2..5: softmax / epilogue
+constexpr int kEpiWarps = 8;                // two groups of four (a warp may only touch TMEM lane quarter warp_id % 4)
+constexpr int kThreads = 32 * (2 + kEpiWarps);   // warp 0: TMA, warp 1: MMA issue + TMEM owner, warps 2..9: softmax / epilogue
 constexpr int kAtomBytes = 128 * 128;      // one [128 rows x 64 bf16] swizzled atom of P / dS
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -101,6 +102,14 @@ __device__ __forceinline__ void store_global64(bf16* dst, const float* v) {
 
 __device__ __forceinline__ int ceil16(int x) { return (x + 15) & ~15; }
 
+// the eight softmax warps only (TMA / MMA warps never join): named barrier 1
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void store_global32(bf16* dst, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[j] = pack8(v + 8 * j);
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 // TMEM: S at columns [0, SkP), O at [384, 448).  smem: Q | K | V | P atoms (ceil(Sk/64) x 16 KB) | barriers.
 __global__ void __launch_bounds__(kThreads, 1)
@@ -118,6 +127,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t *bar_qk = bars, *bar_v = bars + 1, *s_full = bars + 2, *s_free = bars + 3, *o_full = bars + 4, *o_free = bars + 5,
            *p_free = bars + 6, *p_ready = bars + 7;          // p_ready[0..4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* sStat = reinterpret_cast<float*>(bars + 16);      // [2 groups][128 rows] row max, then [2][128] row sum
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
@@ -125,9 +135,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV);
     ptx::mbar_init(bar_qk, 1); ptx::mbar_init(bar_v, 1);
-    ptx::mbar_init(s_full, 1); ptx::mbar_init(s_free, 4);
-    ptx::mbar_init(o_full, 1); ptx::mbar_init(o_free, 4); ptx::mbar_init(p_free, 1);
-    for (int a = 0; a < 5; ++a) ptx::mbar_init(&p_ready[a], 4);
+    ptx::mbar_init(s_full, 1); ptx::mbar_init(s_free, kEpiWarps);
+    ptx::mbar_init(o_full, 1); ptx::mbar_init(o_free, kEpiWarps); ptx::mbar_init(p_free, 1);
+    for (int a = 0; a < 5; ++a) ptx::mbar_init(&p_ready[a], kEpiWarps);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -135,6 +145,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  PDL_GRID_SYNC();   // (PDL build) the set-up above overlapped the previous kernel's tail; global memory is touched below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -184,7 +195,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ---------------------------------------------------------------- softmax / epilogue warps (thread <-> query row)
-    const int q = warp & 3, r = q * 32 + lane;
+    // Two groups of four warps share every tile: group g owns the 32-column chunks c = g, g+2, ... of S (= half g of every 64-key
+    // P atom) and columns [32g, 32g+32) of O; row max / row sum are combined through shared memory.
+    const int q = warp & 3, grp = (warp - 2) >> 2, r = q * 32 + lane;
     const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
     const int nch = (Sk + 31) >> 5;
     const long long bh = static_cast<long long>(b) * p.H + h;
@@ -193,10 +206,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const bool wvalid = i * 128 + q * 32 < Sq, rv = g < Sq;
       wait_bar(s_full, i & 1, 6);
       ptx::tc_fence_after();
-      float m2 = 0.f, l = 0.f;
+      float mx = -INFINITY;
       if (wvalid) {
-        float mx = -INFINITY;
-        for (int c = 0; c < nch; ++c) {
+        for (int c = grp; c < nch; c += 2) {
           uint32_t raw[32];
           ptx::tmem_ld_32x32(trow + c * 32, raw);
           ptx::tmem_ld_wait();
@@ -208,25 +220,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int j = 0; j < 32; ++j) if (c * 32 + j < Sk) mx = fmaxf(mx, __uint_as_float(raw[j]));
           }
         }
-        m2 = mx * p.sl2;                      // scale > 0: max commutes with the scaling
       }
+      sStat[grp * 128 + r] = mx;
+      epi_sync();
+      const float m2 = fmaxf(sStat[r], sStat[128 + r]) * p.sl2;     // scale > 0: max commutes with the scaling
+      float l = 0.f;
       if (i > 0) wait_bar(p_free, (i - 1) & 1, 7);     // P V of the previous tile has finished reading the P atoms
       for (int a = 0; a < nKA; ++a) {
-        if (wvalid) {
-          for (int c = 2 * a; c < min(2 * a + 2, nch); ++c) {
-            uint32_t raw[32];
-            ptx::tmem_ld_32x32(trow + c * 32, raw);
-            ptx::tmem_ld_wait();
-            float v[32];
-            const bool full = c * 32 + 32 <= Sk;
+        const int c = 2 * a + grp;
+        if (wvalid && c < nch) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(trow + c * 32, raw);
+          ptx::tmem_ld_wait();
+          float v[32];
+          const bool full = c * 32 + 32 <= Sk;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float e = ex2(fmaf(__uint_as_float(raw[j]), p.sl2, -m2));
-              if (!full && c * 32 + j >= Sk) e = 0.f;
-              v[j] = e; l += e;
-            }
-            store_row32(sP + a * kAtomBytes, r, (c & 1) * 4, v);
+          for (int j = 0; j < 32; ++j) {
+            float e = ex2(fmaf(__uint_as_float(raw[j]), p.sl2, -m2));
+            if (!full && c * 32 + j >= Sk) e = 0.f;
+            v[j] = e; l += e;
           }
+          store_row32(sP + a * kAtomBytes, r, grp * 4, v);
         }
         ptx::fence_proxy_async();
         __syncwarp();
@@ -235,23 +249,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(s_free);
+      sStat[256 + grp * 128 + r] = l;
+      epi_sync();
+      l = sStat[256 + r] + sStat[384 + r];
       wait_bar(o_full, i & 1, 8);
       ptx::tc_fence_after();
       if (wvalid) {
         uint32_t raw[32];
-        float v[64];
+        float v[32];
         const float inv = 1.0f / l;
-        ptx::tmem_ld_32x32(trow + 384, raw);
+        ptx::tmem_ld_32x32(trow + 384 + 32 * grp, raw);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * inv;
-        ptx::tmem_ld_32x32(trow + 416, raw);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(raw[j]) * inv;
         if (rv) {
-          store_global64(p.o + b * p.o_bs + static_cast<long long>(g) * p.o_rs + h * 64, v);
-          if (p.lse) p.lse[bh * Sq + g] = (m2 + __log2f(l)) * kLn2;
+          store_global32(p.o + b * p.o_bs + static_cast<long long>(g) * p.o_rs + h * 64 + 32 * grp, v);
+          if (p.lse && grp == 0) p.lse[bh * Sq + g] = (m2 + __log2f(l)) * kLn2;
         }
       }
       ptx::tc_fence_before();
@@ -297,9 +310,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     ptx::prefetch_tensormap(&tmQ); ptx::prefetch_tensormap(&tmK); ptx::prefetch_tensormap(&tmV); ptx::prefetch_tensormap(&tmdO);
     ptx::mbar_init(&bar->qk, 1); ptx::mbar_init(&bar->vdo, 1);
     for (int s = 0; s < 3; ++s) { ptx::mbar_init(&bar->slot_full[s], 1); ptx::mbar_init(&bar->slot_free[s], 4); }
-    ptx::mbar_init(&bar->p_ready, 4); ptx::mbar_init(&bar->p_free, 1);
-    ptx::mbar_init(&bar->ds_ready, 4); ptx::mbar_init(&bar->ds_free, 1);
-    ptx::mbar_init(&bar->dkv_full, 1); ptx::mbar_init(&bar->dkv_free, 4);
+    ptx::mbar_init(&bar->p_ready, kEpiWarps); ptx::mbar_init(&bar->p_free, 1);
+    ptx::mbar_init(&bar->ds_ready, kEpiWarps); ptx::mbar_init(&bar->ds_free, 1);
+    ptx::mbar_init(&bar->dkv_full, 1); ptx::mbar_init(&bar->dkv_free, kEpiWarps);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(&bar->tmem_slot);
@@ -307,6 +320,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bar->tmem_slot;
+  PDL_GRID_SYNC();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -381,7 +395,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     stage_dk_dq(T - 1);
   } else {
     // ---------------------------------------------------------------- softmax-backward / epilogue warps (thread <-> tile row)
-    const int q = warp & 3, r = q * 32 + lane;
+    // Two groups of four warps: group g consumes the ring items of key half g of every tile (S^g then dP^g, issued by the MMA warp in
+    // the order S^0 dP^0 S^1 dP^1), writes atom g of P / dS, reads out dK (g = 0) or dV (g = 1) and columns [32g, 32g+32) of dQ.
+    const int q = warp & 3, grp = (warp - 2) >> 2, r = q * 32 + lane;
     const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
     const long long bh = static_cast<long long>(b) * p.H + h;
     // per-row statistics of the (up to three) query tiles: log2-domain LSE and delta = rowsum(dO * O)
@@ -404,47 +420,31 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         dlt[i] = acc;
       }
     }
-    int k = 0;
     float pr[64];                                                // probabilities of the current (tile, half), fp32
-    auto wait_item = [&](uint32_t (&raw)[64], bool wvalid) {
-      const int slot = k % 3, n = k / 3;
-      wait_bar(&bar->slot_full[slot], n & 1, 15);
-      ptx::tc_fence_after();
-      if (wvalid) {
-        uint32_t lo[32], hi[32];
-        ptx::tmem_ld_32x32(trow + 320 + 64 * slot, lo);
-        ptx::tmem_ld_32x32(trow + 320 + 64 * slot + 32, hi);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) { raw[c] = lo[c]; raw[32 + c] = hi[c]; }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bar->slot_free[slot]);    // the accumulator is in registers: the slot may be refilled
-      ++k;
-    };
-    auto readout64 = [&](uint32_t col, bf16* dst, bool ok) {
-      uint32_t lo[32], hi[32];
-      ptx::tmem_ld_32x32(trow + col, lo);
-      ptx::tmem_ld_32x32(trow + col + 32, hi);
+    auto readout32 = [&](uint32_t col, bf16* dst, bool ok) {
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(trow + col, raw);
       ptx::tmem_ld_wait();
-      float v[64];
+      float v[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) { v[c] = __uint_as_float(lo[c]); v[32 + c] = __uint_as_float(hi[c]); }
-      if (ok) store_global64(dst, v);
+      for (int c = 0; c < 32; ++c) v[c] = __uint_as_float(raw[c]);
+      if (ok) store_global32(dst, v);
     };
-    auto readout_dkv = [&](int j) {
+    auto readout_dkv = [&](int j) {                              // group 0: dK_j, group 1: dV_j
       wait_bar(&bar->dkv_full, j & 1, 16);
       ptx::tc_fence_after();
       const int g = 128 * j + r;
       if (128 * j + 32 * q < Sk) {
-        readout64(192, p.dk + b * p.dk_bs + static_cast<long long>(g) * p.dk_rs + h * 64, g < Sk);
-        readout64(256, p.dv + b * p.dv_bs + static_cast<long long>(g) * p.dv_rs + h * 64, g < Sk);
+        bf16* dst = grp == 0 ? p.dk + b * p.dk_bs + static_cast<long long>(g) * p.dk_rs + h * 64
+                             : p.dv + b * p.dv_bs + static_cast<long long>(g) * p.dv_rs + h * 64;
+        readout32(192 + 64 * grp, dst, g < Sk);
+        readout32(192 + 64 * grp + 32, dst + 32, g < Sk);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bar->dkv_free);
     };
+    int kbase = 0;                                               // ring index of this tile's first item
     for (int t = 0; t < T; ++t) {
       const int j = t / nTq, i = t % nTq;
       const int g = 128 * i + r;
@@ -452,49 +452,71 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float l2 = i == 0 ? lse2[0] : (i == 1 ? lse2[1] : lse2[2]);
       const float dl = i == 0 ? dlt[0] : (i == 1 ? dlt[1] : dlt[2]);
       const int nh = (128 * j + 64 < Sk) ? 2 : 1;
-      for (int hh = 0; hh < nh; ++hh) {
-        uint32_t raw[64];
-        // ---- S^h -> P^h
-        wait_item(raw, wvalid);
-        if (hh == 0 && t > 0) wait_bar(&bar->p_free, (t - 1) & 1, 17);
-        if (wvalid) {
-          const int k0 = 128 * j + 64 * hh;
+      const bool mine = grp < nh;                                // this group's key half exists in this tile
+      if (t > 0) wait_bar(&bar->p_free, (t - 1) & 1, 17);        // dV of the previous tile has read the P atoms
+      if (mine) {
+        // ---- S^g -> P^g
+        const int k = kbase + 2 * grp, slot = k % 3;
+        wait_bar(&bar->slot_full[slot], (k / 3) & 1, 15);
+        ptx::tc_fence_after();
+        const int k0 = 128 * j + 64 * grp;
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            float e = ex2(fmaf(__uint_as_float(raw[c]), p.sl2, -l2));
-            pr[c] = (rv && k0 + c < Sk) ? e : 0.f;
+        for (int half = 0; half < 2; ++half) {
+          if (wvalid) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(trow + 320 + 64 * slot + 32 * half, raw);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float e = ex2(fmaf(__uint_as_float(raw[c]), p.sl2, -l2));
+              pr[32 * half + c] = (rv && k0 + 32 * half + c < Sk) ? e : 0.f;
+            }
+            store_row32(sP + grp * kAtomBytes, r, 4 * half, pr + 32 * half);
           }
-          store_row32(sP + hh * kAtomBytes, r, 0, pr);
-          store_row32(sP + hh * kAtomBytes, r, 4, pr + 32);
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar->slot_free[slot]);  // the accumulator is in registers: the slot may be refilled
         ptx::fence_proxy_async();
-        if (hh == nh - 1) {
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bar->p_ready);
-        }
-        // ---- dP^h -> dS^h = P * (dP - delta) * scale
-        wait_item(raw, wvalid);
-        if (hh == 0 && t > 0) wait_bar(&bar->ds_free, (t - 1) & 1, 18);
-        if (wvalid) {
-          float ds[64];
-#pragma unroll
-          for (int c = 0; c < 64; ++c) ds[c] = pr[c] == 0.f ? 0.f : pr[c] * (__uint_as_float(raw[c]) - dl) * p.scale;
-          store_row32(sdS + hh * kAtomBytes, r, 0, ds);
-          store_row32(sdS + hh * kAtomBytes, r, 4, ds + 32);
-        }
-        ptx::fence_proxy_async();
-        if (hh == nh - 1) {
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bar->ds_ready);
-        }
-        if (hh == 0 && i == 0 && j > 0) readout_dkv(j - 1);      // mirrors the issuer: dK/dV of key tile j-1 are complete here
       }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar->p_ready);
+      if (t > 0) wait_bar(&bar->ds_free, (t - 1) & 1, 18);       // dK / dQ of the previous tile have read the dS atoms
+      if (mine) {
+        // ---- dP^g -> dS^g = P * (dP - delta) * scale
+        const int k = kbase + 2 * grp + 1, slot = k % 3;
+        wait_bar(&bar->slot_full[slot], (k / 3) & 1, 15);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (wvalid) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(trow + 320 + 64 * slot + 32 * half, raw);
+            ptx::tmem_ld_wait();
+            float ds[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float pv = pr[32 * half + c];
+              ds[c] = pv == 0.f ? 0.f : pv * (__uint_as_float(raw[c]) - dl) * p.scale;
+            }
+            store_row32(sdS + grp * kAtomBytes, r, 4 * half, ds);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar->slot_free[slot]);
+        ptx::fence_proxy_async();
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bar->ds_ready);
+      if (i == 0 && j > 0) readout_dkv(j - 1);                   // dK / dV of key tile j-1 are complete (the issuer committed dkv_full)
+      kbase += 2 * nh;
     }
     readout_dkv(nTk - 1);                                        // its commit also covers every dQ product
     for (int i = 0; i < nTq; ++i) {
       const int g = 128 * i + r;
       if (128 * i + 32 * q < Sq)
-        readout64(64 * i, p.dq + b * p.dq_bs + static_cast<long long>(g) * p.dq_rs + h * 64, g < Sq);
+        readout32(64 * i + 32 * grp, p.dq + b * p.dq_bs + static_cast<long long>(g) * p.dq_rs + h * 64 + 32 * grp, g < Sq);
     }
   }
   ptx::tc_fence_before();
@@ -552,7 +574,7 @@ int make_map(CUtensorMap* map, const void* base, long long bs, long long rs, int
 }
 
 int up16(int x) { return (x + 15) & ~15; }
-int fwd_smem(int Sq, int Sk) { return (up16(Sq) + 2 * up16(Sk)) * 128 + ((Sk + 63) / 64) * kAtomBytes + 256 + 1024; }
+int fwd_smem(int Sq, int Sk) { return (up16(Sq) + 2 * up16(Sk)) * 128 + ((Sk + 63) / 64) * kAtomBytes + 128 + 2048 + 1024; }
 int bwd_smem(int Sq, int Sk) { return 2 * (up16(Sq) + up16(Sk)) * 128 + 4 * kAtomBytes + 256 + 1024; }
 
 int g_force_legacy = 0;
@@ -600,7 +622,7 @@ int attn_sm100_try_fwd(const PrismerAttnArgs* a, cudaStream_t stream, int* rc_ou
     }
     configured = true;
   }
-  attn_fwd_tc_kernel<<<a->B * a->H, kThreads, fwd_smem(a->Lq, a->Lk), stream>>>(tq, tk, tv, p);
+  pdl_launch(attn_fwd_tc_kernel, dim3(a->B * a->H), dim3(kThreads), static_cast<size_t>(fwd_smem(a->Lq, a->Lk)), stream, tq, tk, tv, p);
   *rc_out = LAUNCH_CHECK();
   return 1;
 }
@@ -629,7 +651,7 @@ int attn_sm100_try_bwd(const PrismerAttnArgs* a, cudaStream_t stream, int* rc_ou
     }
     configured = true;
   }
-  attn_bwd_tc_kernel<<<a->B * a->H, kThreads, bwd_smem(a->Lq, a->Lk), stream>>>(tq, tk, tv, tdo, p);
+  pdl_launch(attn_bwd_tc_kernel, dim3(a->B * a->H), dim3(kThreads), static_cast<size_t>(bwd_smem(a->Lq, a->Lk)), stream, tq, tk, tv, tdo, p);
   *rc_out = LAUNCH_CHECK();
   return 1;
 }

@@ -1,0 +1,278 @@
+// KV-cached single-token decode step (replaces the reference's cache-less re-forward of the whole prefix,
+// roberta.py:401-406 driven from prismer_caption.py:45-50): the kernels a decoder layer needs when every sequence contributes ONE new
+// token (M = batch [* beams] rows, typically 32).  At that size every product is a weight-streaming, launch-latency-bound "skinny"
+// GEMM -- 348 MB of bf16 weights per step for Prismer-BASE against 11 GFLOP -- so these are small mma.sync kernels with no TMA /
+// TMEM / mbarrier prologue (a 148-CTA persistent tcgen05 GEMM spends longer setting up than this whole product takes):
+//
+//   skinny_linear : y[M,N] = act(x[M,K] . W[N,K]^T + bias) (+ residual);  32 rows x 16 columns per CTA, the 4 warps split K, weights
+//                   go global -> mma B fragments directly (32-byte sectors fully used), x is staged once in shared memory.
+//                   Optional fused post-LayerNorm (roberta.py:139,182): the LAST CTA to finish normalises the completed rows
+//                   (fp32 statistics, eps as given) -> the kernel emits both the pre-LN sum and LN(pre) without a second launch.
+//   decode_attn   : one query per (batch, head) over a K/V cache (self-attention: the new token's k / v are appended to the cache in the
+//                   same kernel) or over the projected visual tokens (cross-attention); one warp per (batch, head).
+#include "common.cuh"
+#include "prismer_sm100.h"
+
+namespace {
+
+constexpr int kRows = 32;        // rows per CTA (two m16 tiles)
+constexpr int kCols = 16;        // columns per CTA (two n8 tiles)
+constexpr int kKc = 1024;        // K chunk staged in shared memory
+constexpr int kPad = 8;
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+
+// L1-bypassing load: the rows were written by OTHER CTAs of this launch (made visible by their __threadfence + the atomic counter)
+__device__ __forceinline__ float ldcg_bf16(const bf16* p) {
+  return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
+}
+
+struct SkinnyParams {
+  const bf16* x; long long ldx;
+  const bf16* w; long long ldw;
+  const float* bias;
+  const bf16* residual; long long ldr;
+  void* out; long long ldo; int out_fp32;
+  bf16* ln_out; long long ldln; const float* gamma; const float* beta; float eps;
+  unsigned int* counter;          // [gridDim.y] self-resetting arrival counters (fused LayerNorm only)
+  int M, N, K, act;
+};
+
+__global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sx = reinterpret_cast<bf16*>(smem_raw);
+  __shared__ unsigned int s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kCols, m0 = blockIdx.y * kRows;
+  const int mrows = min(kRows, p.M - m0);
+  float acc[2][2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
+  // this lane's two weight rows (n8 tiles 0 and 1); rows past N are clamped and their results discarded
+  const int nrow0 = min(n0 + (lane >> 2), p.N - 1), nrow1 = min(n0 + 8 + (lane >> 2), p.N - 1);
+  const bf16* w0 = p.w + static_cast<long long>(nrow0) * p.ldw + 2 * (lane & 3);
+  const bf16* w1 = p.w + static_cast<long long>(nrow1) * p.ldw + 2 * (lane & 3);
+
+  for (int kc = 0; kc < p.K; kc += kKc) {
+    const int kn = min(kKc, p.K - kc);                     // multiple of 16 (checked on the host)
+    const int ld = kn + kPad;
+    if (kc > 0) __syncthreads();
+    for (int i = threadIdx.x; i < kRows * (kn >> 3); i += 128) {
+      const int r = i / (kn >> 3), c = i % (kn >> 3);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r < mrows) v = *reinterpret_cast<const uint4*>(p.x + static_cast<long long>(m0 + r) * p.ldx + kc + c * 8);
+      *reinterpret_cast<uint4*>(sx + r * ld + c * 8) = v;
+    }
+    __syncthreads();
+    const int steps = kn >> 4;
+#pragma unroll 4
+    for (int s = warp; s < steps; s += 4) {
+      const int k = kc + s * 16;
+      const uint32_t b00 = __ldg(reinterpret_cast<const unsigned int*>(w0 + k)), b01 = __ldg(reinterpret_cast<const unsigned int*>(w0 + k + 8));
+      const uint32_t b10 = __ldg(reinterpret_cast<const unsigned int*>(w1 + k)), b11 = __ldg(reinterpret_cast<const unsigned int*>(w1 + k + 8));
+      uint32_t a0[4], a1[4];
+      ldsm_x4(a0, sx + (lane & 15) * ld + s * 16 + (lane >> 4) * 8);
+      ldsm_x4(a1, sx + (16 + (lane & 15)) * ld + s * 16 + (lane >> 4) * 8);
+      mma16816(acc[0][0], a0, b00, b01);
+      mma16816(acc[0][1], a0, b10, b11);
+      mma16816(acc[1][0], a1, b00, b01);
+      mma16816(acc[1][1], a1, b10, b11);
+    }
+  }
+  // cross-warp reduction of the split-K partials through shared memory: red[warp][row][col]
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(smem_raw);
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = mt * 16 + (lane >> 2) + (e >> 1) * 8, c = nt * 8 + 2 * (lane & 3) + (e & 1);
+        red[(warp * kRows + r) * kCols + c] = acc[mt][nt][e];
+      }
+  __syncthreads();
+  for (int o = threadIdx.x; o < kRows * kCols; o += 128) {
+    const int r = o / kCols, c = o % kCols;
+    const int m = m0 + r, n = n0 + c;
+    if (r >= mrows || n >= p.N) continue;
+    float v = red[o] + red[kRows * kCols + o] + red[2 * kRows * kCols + o] + red[3 * kRows * kCols + o];
+    if (p.bias) v += p.bias[n];
+    v = act_fwd(p.act, v);
+    if (p.residual) v += __bfloat162float(p.residual[static_cast<long long>(m) * p.ldr + n]);
+    if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<long long>(m) * p.ldo + n] = v;
+    else reinterpret_cast<bf16*>(p.out)[static_cast<long long>(m) * p.ldo + n] = __float2bfloat16(v);
+  }
+  if (!p.ln_out) return;
+  // ---- fused LayerNorm: the last CTA of this row group to arrive normalises the (now complete) rows
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(p.counter + blockIdx.y, 1u);
+    s_last = (prev == gridDim.x - 1) ? 1u : 0u;
+    if (s_last) p.counter[blockIdx.y] = 0;                  // ready for the next launch (stream-ordered)
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const bf16* pre = reinterpret_cast<const bf16*>(p.out);   // fused LayerNorm requires a bf16 `out`
+  for (int r = warp; r < mrows; r += 4) {
+    const bf16* row = pre + static_cast<long long>(m0 + r) * p.ldo;
+    float sum = 0.f;
+    for (int c = lane; c < p.N; c += 32) sum += ldcg_bf16(row + c);
+    const float mean = warp_sum(sum) / p.N;
+    float var = 0.f;
+    for (int c = lane; c < p.N; c += 32) {
+      const float d = ldcg_bf16(row + c) - mean;
+      var += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(var) / p.N + p.eps);
+    bf16* dst = p.ln_out + static_cast<long long>(m0 + r) * p.ldln;
+    for (int c = lane; c < p.N; c += 32) {
+      const float xv = ldcg_bf16(row + c);
+      dst[c] = __float2bfloat16((xv - mean) * rstd * p.gamma[c] + p.beta[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ single-query attention
+struct DecAttnParams {
+  const bf16* q; long long q_bs;                   // [B, H*64] new-token queries
+  const bf16* k; const bf16* v; long long kv_bs, kv_rs;   // keys / values: base + b*bs + j*rs + h*64, j < len
+  int len;
+  const bf16* k_new; const bf16* v_new; long long new_bs;  // self-attention: the new token's k / v (key index `len`), appended to ...
+  bf16* k_cache; bf16* v_cache; long long c_bs, c_rs;      // ... the cache at row `len`
+  const long long* key_mask; int mask_ld;          // [B, >= len+1] 1 = attend (prompt padding), or null
+  bf16* o; long long o_bs;
+  int B, H;
+  float scale;
+};
+
+// one warp per (batch, head); head dim 64.  Scores in fp32, probabilities rounded to bf16 before P.V like the tensor-core kernels.
+__global__ void __launch_bounds__(128) decode_attn_kernel(DecAttnParams p) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= p.B * p.H) return;
+  const int b = wid / p.H, h = wid % p.H;
+  const int total = p.len + (p.k_new ? 1 : 0);
+  // q: every lane keeps the whole 64-vector (8 x 16 B, broadcast loads)
+  float qv[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(p.q + b * p.q_bs + h * 64);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) unpack8(qp[c], qv + 8 * c);
+  }
+  auto key_ptr = [&](int j) -> const bf16* {
+    return j < p.len ? p.k + b * p.kv_bs + static_cast<long long>(j) * p.kv_rs + h * 64 : p.k_new + b * p.new_bs + h * 64;
+  };
+  auto val_ptr = [&](int j) -> const bf16* {
+    return j < p.len ? p.v + b * p.kv_bs + static_cast<long long>(j) * p.kv_rs + h * 64 : p.v_new + b * p.new_bs + h * 64;
+  };
+  // scores: lane handles keys lane, lane+32, ... (up to 10 per lane: Lk <= 320)
+  float sc[10];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int j = lane + 32 * i;
+    sc[i] = -INFINITY;
+    if (j < total && !(p.key_mask && p.key_mask[static_cast<long long>(b) * p.mask_ld + j] == 0)) {
+      const uint4* kp = reinterpret_cast<const uint4*>(key_ptr(j));
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float kv[8];
+        unpack8(kp[c], kv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = fmaf(qv[8 * c + e], kv[e], acc);
+      }
+      sc[i] = acc * p.scale;
+      mx = fmaxf(mx, sc[i]);
+    }
+  }
+  mx = warp_max(mx);
+  const float msafe = mx == -INFINITY ? 0.f : mx;
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float e = sc[i] == -INFINITY ? 0.f : __expf(sc[i] - msafe);
+    l += e;
+    sc[i] = __bfloat162float(__float2bfloat16(e));
+  }
+  l = warp_sum(l);
+  // O = sum_j P_j V_j: lane owns channels 2*lane, 2*lane+1
+  float o0 = 0.f, o1 = 0.f;
+  for (int j = 0; j < total; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31);   // sc index is warp-uniform per j
+    if (pj != 0.f) {
+      const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(val_ptr(j) + 2 * lane);
+      o0 = fmaf(pj, __bfloat162float(vv.x), o0);
+      o1 = fmaf(pj, __bfloat162float(vv.y), o1);
+    }
+  }
+  const float inv = l > 0.f ? 1.0f / l : 0.f;
+  *reinterpret_cast<__nv_bfloat162*>(p.o + b * p.o_bs + h * 64 + 2 * lane) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+  if (p.k_new) {   // append the new token's k / v to the cache (row `len`)
+    bf16* kc = p.k_cache + b * p.c_bs + static_cast<long long>(p.len) * p.c_rs + h * 64;
+    bf16* vc = p.v_cache + b * p.c_bs + static_cast<long long>(p.len) * p.c_rs + h * 64;
+    *reinterpret_cast<__nv_bfloat162*>(kc + 2 * lane) = *reinterpret_cast<const __nv_bfloat162*>(p.k_new + b * p.new_bs + h * 64 + 2 * lane);
+    *reinterpret_cast<__nv_bfloat162*>(vc + 2 * lane) = *reinterpret_cast<const __nv_bfloat162*>(p.v_new + b * p.new_bs + h * 64 + 2 * lane);
+  }
+}
+
+}  // namespace
+
+extern "C" int prismer_skinny_linear(const void* x, long long ldx, const void* w, long long ldw, const float* bias, const void* residual,
+                                     long long ldr, void* out, long long ldo, int out_fp32, void* ln_out, long long ldln,
+                                     const float* gamma, const float* beta, float eps, unsigned int* counter, int M, int N, int K, int act,
+                                     cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 16) || (ldx % 8) || (ldw % 2)) return PRISMER_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 3)) return PRISMER_ERR_ALIGN;
+  if (ln_out && (out_fp32 || !gamma || !beta || !counter)) return PRISMER_ERR_SHAPE;
+  SkinnyParams p;
+  p.x = reinterpret_cast<const bf16*>(x); p.ldx = ldx; p.w = reinterpret_cast<const bf16*>(w); p.ldw = ldw; p.bias = bias;
+  p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
+  p.ln_out = reinterpret_cast<bf16*>(ln_out); p.ldln = ldln; p.gamma = gamma; p.beta = beta; p.eps = eps; p.counter = counter;
+  p.M = M; p.N = N; p.K = K; p.act = act;
+  const int kc = K < kKc ? K : kKc;
+  size_t smem = static_cast<size_t>(kRows) * (kc + kPad) * 2;
+  const size_t red = static_cast<size_t>(4) * kRows * kCols * 4;
+  if (smem < red) smem = red;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRows * (kKc + kPad) * 2) != cudaSuccess)
+      return PRISMER_ERR_CUDA;
+    configured = true;
+  }
+  dim3 grid((N + kCols - 1) / kCols, (M + kRows - 1) / kRows);
+  skinny_linear_kernel<<<grid, 128, smem, stream>>>(p);
+  return LAUNCH_CHECK();
+}
+
+extern "C" int prismer_decode_attention(const void* q, long long q_bs, const void* k, const void* v, long long kv_bs, long long kv_rs,
+                                        int len, const void* k_new, const void* v_new, long long new_bs, void* k_cache, void* v_cache,
+                                        long long c_bs, long long c_rs, const void* key_mask, int mask_ld, void* o, long long o_bs, int B,
+                                        int H, int d, float scale, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || d != 64 || len < 0 || len + (k_new ? 1 : 0) > 320 || len + (k_new ? 1 : 0) <= 0) return PRISMER_ERR_SHAPE;
+  if ((q_bs % 8) || (kv_bs % 8) || (kv_rs % 8) || (o_bs % 2)) return PRISMER_ERR_ALIGN;
+  if ((k_new != nullptr) != (v_new != nullptr) || (k_new && (!k_cache || !v_cache))) return PRISMER_ERR_SHAPE;
+  DecAttnParams p;
+  p.q = reinterpret_cast<const bf16*>(q); p.q_bs = q_bs;
+  p.k = reinterpret_cast<const bf16*>(k); p.v = reinterpret_cast<const bf16*>(v); p.kv_bs = kv_bs; p.kv_rs = kv_rs; p.len = len;
+  p.k_new = reinterpret_cast<const bf16*>(k_new); p.v_new = reinterpret_cast<const bf16*>(v_new); p.new_bs = new_bs;
+  p.k_cache = reinterpret_cast<bf16*>(k_cache); p.v_cache = reinterpret_cast<bf16*>(v_cache); p.c_bs = c_bs; p.c_rs = c_rs;
+  p.key_mask = reinterpret_cast<const long long*>(key_mask); p.mask_ld = mask_ld;
+  p.o = reinterpret_cast<bf16*>(o); p.o_bs = o_bs; p.B = B; p.H = H; p.scale = scale;
+  const int warps = B * H;
+  decode_attn_kernel<<<(warps + 3) / 4, 128, 0, stream>>>(p);
+  return LAUNCH_CHECK();
+}

@@ -23,6 +23,7 @@ ln_bwd2_kernel(const bf16* __restrict__ dy, long long lddy, const bf16* __restri
                long long lddz, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D, float drop_p, uint32_t thr16,
                const unsigned long long* seed, uint32_t rng_stream) {
   extern __shared__ float red[];  // HAS_DG: [kWarps][2][D]
+  PDL_GRID_SYNC();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   float* rg = red + warp * 2 * D;
@@ -143,7 +144,7 @@ int launch_ln2(const void* dy, long long lddy, const void* x, long long ldx, con
   const int cap = 148 * (HAS_DG ? 2 : 3) * 2;                  // two waves of the resident blocks
   if (grid > cap) grid = cap;
   const uint32_t thr16 = static_cast<uint32_t>(drop_p * 65536.0f + 0.5f);
-  ln_bwd2_kernel<VPL, HAS_DG><<<grid, kWarps * 32, smem, stream>>>(
+  pdl_launch(ln_bwd2_kernel<VPL, HAS_DG>, dim3(grid), dim3(kWarps * 32), smem, stream,
       reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(x), ldx, mean, rstd, gamma,
       reinterpret_cast<const bf16*>(dres), lddres, reinterpret_cast<bf16*>(dx), lddx, reinterpret_cast<bf16*>(dz), lddz, dgamma, dbeta, rows,
       D, drop_p, thr16, seed, rng_stream);

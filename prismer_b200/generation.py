@@ -2,17 +2,31 @@
 
 Greedy follows HF greedy search as the reference drives it: ``logits[:, -1]`` -> MinLength processor (eos = -inf while
 cur_len < min_length) -> argmax (device kernel, lowest index on ties) -> finished rows emit pad -> stop at max_length
-or when every row has produced eos.  The per-step decoder pass re-runs on the full prefix exactly like the reference's
-cache-less ``prepare_inputs_for_generation`` (roberta.py:401-406); the cross-attention K/V projections of the visual
-tokens are computed once per call instead of once per step and layer."""
+or when every row has produced eos.  Two schedules compute the per-step logits:
+
+* ``KV_CACHE = True`` (default): one new token per sequence and step against per-layer K/V caches (``kv_decode.py``,
+  ``csrc/decode.cu``; SURVEY.md K16) -- the algorithmic 13.6 GFLOP/img instead of the reference's 178;
+* ``KV_CACHE = False``: the decoder re-runs on the full prefix every step exactly like the reference's cache-less
+  ``prepare_inputs_for_generation`` (roberta.py:401-406) -- kept as the in-repo cross-check of the cached path (and used by beam search).
+
+In both, the cross-attention K/V projections of the visual tokens are computed once per call instead of once per step and layer."""
 from __future__ import annotations
 
 import torch
 
-from . import engine, ops
+from . import engine, kv_decode, ops
+
+KV_CACHE = True
 
 
 def _greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None, prompt_mask=None):
+    cfg = dec.config
+    if KV_CACHE and cfg.hidden_size // cfg.num_attention_heads == 64 and enc.shape[1] <= 320:
+        return kv_decode.greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps, prompt_mask)
+    return _greedy_loop_nocache(dec, ids, T0, enc, max_length, min_length, early_exit, steps, prompt_mask)
+
+
+def _greedy_loop_nocache(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None, prompt_mask=None):
     """Device-side greedy loop on a preallocated ``ids`` [B, max_length] buffer (prefix already in columns [0, T0)).
     With ``early_exit=False`` there is no host synchronisation at all (finished rows keep emitting pad), so the whole loop
     can be captured in a CUDA graph."""

@@ -140,6 +140,7 @@ def test_product_greedy_loop_matches_reference_with_a_stand_in_engine(c, templat
     monkeypatch.setattr(engine, "decoder_forward", fake_decoder_forward)
     monkeypatch.setattr(engine, "_store", lambda m: SimpleNamespace(refresh=lambda: None))
     monkeypatch.setattr(ops, "argmax", fake_argmax)
+    monkeypatch.setattr(generation, "KV_CACHE", False)       # the cache-less loop is the one that calls decoder_forward per step
     dec = SimpleNamespace(config=SimpleNamespace(eos_token_id=TINY_DEC["eos_token_id"], pad_token_id=TINY_DEC["pad_token_id"],
                                                  vocab_size=TINY_DEC["vocab_size"]))
     out = generation.greedy(dec, ids, enc, mask, max_length=c["T0"] + c["max_add"], min_length=c["T0"] + c["min_add"])

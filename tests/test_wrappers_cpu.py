@@ -56,7 +56,8 @@ def stand_in(monkeypatch):
                          decoder_forward=decoder_forward, _experts_check=lambda e: None,
                          _store=lambda m: SimpleNamespace(refresh=lambda: None)).items():
         monkeypatch.setattr(engine, name, fn)
-    from prismer_b200 import ops
+    from prismer_b200 import generation, ops
+    monkeypatch.setattr(generation, "KV_CACHE", False)     # the stand-ins replace decoder_forward: the cache-less schedule calls it per step
     monkeypatch.setattr(ops, "argmax", lambda last, V, suppress_eos=False, eos=2: (
         last.masked_fill(torch.arange(last.shape[1]) == eos, -float("inf")) if suppress_eos else last)[:, :V].argmax(-1))
 
