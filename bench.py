@@ -25,11 +25,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 EXPERTS = ["depth", "normal", "seg_coco", "edge", "obj_detection", "ocr_detection"]
-TRAIN_GFLOP_PER_IMG = 263.1      # BASELINE.md section 3 / SURVEY.md section 8d (freeze_vision, T = 30)
-# secondary row (the reference's real setting image_resolution 480, S = 964): fwd 295.2 G (ViT 225.3, stems
-# 16.3, resampler 15.7, decoder 35.6, LM head 2.35); step = 3 x fwd - 163.8 (frozen ViT wgrad) = 721.8 GFLOP/img
-TRAIN_GFLOP_PER_IMG_480 = 721.8
-FWD_GFLOP_PER_IMG = 102.4
+# Workloads (BASELINE.json configs; step GFLOP/img from BASELINE.md section 3 / SURVEY.md section 8d).  `--config` picks one; the default
+# is the configuration BASELINE.json's metric is quoted on (config 3 at its per-GPU size).
+CONFIGS = {
+    "base_caption224": dict(model="prismer_base", res=224, freeze="freeze_vision", T=30, batch=32, gflop=263.1,
+                            metric="Prismer-BASE caption-train images/sec",
+                            workload="Prismer-BASE caption fine-tune step (fwd+bwd+1 grad all-reduce+AdamW), 224x224 + 6 expert maps, T=30, "
+                                     "freeze_vision, dropout 0.1"),
+    # the reference's real fine-tune resolution (configs/caption.yaml:6; S = 964): fwd 295.2 G; step = 3 x fwd - 163.8 (frozen ViT wgrad)
+    "base_caption480": dict(model="prismer_base", res=480, freeze="freeze_vision", T=30, batch=32, gflop=721.8,
+                            metric="Prismer-BASE caption-train images/sec (480 px)",
+                            workload="Prismer-BASE caption fine-tune step, 480x480 + 6 expert maps, T=30, freeze_vision, dropout 0.1"),
+    # BASELINE.json config 5 (configs/pretrain.yaml:11-14): 32/GPU x 32 GPUs = 1024 in the reference; here 64 per GPU (weak scaling)
+    "large_pretrain224": dict(model="prismer_large", res=224, freeze="freeze_lang_vision", T=30, batch=64, gflop=887.1,
+                              metric="Prismer-LARGE pretrain images/sec",
+                              workload="Prismer-LARGE pretrain LM-loss step (fwd+bwd+1 grad all-reduce+AdamW), 224x224 + 6 expert maps, T=30, "
+                                       "freeze_lang_vision, dropout 0.1"),
+    # BASELINE.json config 4 (configs/vqa.yaml:6-10): 8 per GPU, 480 px, question+answer T = 40
+    "large_vqa480": dict(model="prismer_large", res=480, freeze="freeze_vision", T=40, batch=8, gflop=2987.8,
+                         metric="Prismer-LARGE VQA fine-tune images/sec (480 px)",
+                         workload="Prismer-LARGE VQA fine-tune step, 480x480 + 6 expert maps, T=40 (labels on the 5-token answer span), "
+                                  "freeze_vision, dropout 0.1"),
+}
 
 
 def peaks():
@@ -126,40 +143,45 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    wl = CONFIGS[args.config]
+    B = args.batch or wl["batch"]
+    T = wl["T"]
+    compact = not args.reference_inputs
     torch.manual_seed(0)
-    cfg = {"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": args.resolution, "freeze": "freeze_vision"}
+    cfg = {"experts": EXPERTS, "prismer_model": wl["model"], "image_resolution": wl["res"], "freeze": wl["freeze"]}
     model = PrismerCaption(cfg)
     model.to(dev)
     st = engine.prepare(model, dev)
     if world > 1:
         dist.broadcast(st.master_t, 0); dist.broadcast(st.master_f, 0); st.refresh(force=True)
     opt = FusedAdamW(model, lr=5e-5, weight_decay=0.05, grad_scale=1.0 / world)
-    ex_h, ids_h, mask_h = build_inputs(B, 1000 + rank, compact=args.compact_inputs, resolution=args.resolution)
+    ex_h, ids_h, mask_h = build_inputs(B, 1000 + rank, T=T, compact=compact, resolution=wl["res"])
     ex_h = pin(ex_h); ids_h, mask_h = ids_h.pin_memory(), mask_h.pin_memory()
     ex_d = synthetic.experts_to(ex_h, dev); ids_d, mask_d = ids_h.to(dev), mask_h.to(dev)
     h2d = nbytes(ex_h) + ids_h.numel() * 8 + mask_h.numel() * 8
 
     if args.mode == "caption":
-        return run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d)
+        out = run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d, compact)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        return
 
     model.train()
     labels_d = ids_d.masked_fill(ids_d == 1, -100)
-    labels_d[:, :4] = -100                                   # prismer_caption.py:22-26 (prefix "A picture of" -> 4 ids)
+    if args.config == "large_vqa480":
+        labels_d[:, :T - 5] = -100                           # prismer_vqa.py:32-33: only the answer span is supervised
+    else:
+        labels_d[:, :4] = -100                               # prismer_caption.py:22-26 (prefix "A picture of" -> 4 ids)
     labels_h = labels_d.cpu().pin_memory()
     graphed = None
     if not args.eager:
-        graphed = engine.GraphedTrainStep(model, ex_d, ids_d, mask_d, labels_d, overlap=world > 1 or args.overlap_optimizer)
+        graphed = engine.GraphedTrainStep(model, ex_d, ids_d, mask_d, labels_d, overlap=world > 1)
     comm = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)) if world > 1 else None
 
     def step(ex, ids, mask, host_inputs=False):
         if graphed is not None:
             if host_inputs:                                  # pinned host -> static device buffers (H2D inside the step)
                 graphed.load_inputs(ex, ids, mask, labels_h)
-            if args.overlap_optimizer:                       # experiment: AdamW of the decoder slice overlaps the encoder backward
-                loss = graphed(comm, on_decoder_grads=lambda: opt.step_range(0, st.n_train_dec, True, False))
-                opt.step_range(st.n_train_dec, st.n_train, False, True)
-                return loss
             loss = graphed(comm)                             # fwd + bwd as CUDA graph(s); grads all-reduced, decoder slice early
             opt.step()
             return loss
@@ -208,6 +230,8 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=dev)
     staging = {"ex": synthetic.experts_to(ex_h, dev), "ids": ids_h.to(dev), "mask": mask_h.to(dev), "labels": labels_h.to(dev)}
     h2d_done, consumed = torch.cuda.Event(), torch.cuda.Event()
+    has_inst = "obj_detection" in staging["ex"]
+    pres = {"next": None}
 
     def prefetch():
         with torch.cuda.stream(copy_stream):
@@ -215,13 +239,15 @@ def run_ours(args):
             engine.copy_experts_(staging["ex"], ex_h, non_blocking=True)
             staging["ids"].copy_(ids_h, non_blocking=True); staging["mask"].copy_(mask_h, non_blocking=True)
             staging["labels"].copy_(labels_h, non_blocking=True)
+            if has_inst:     # which instance ids the batch holds (vit.py:144): computed behind the H2D copy, a step ahead of its use
+                pres["next"] = engine.InstancePresence(dev).request(engine.instance_map(staging["ex"]["obj_detection"]), copy_stream)
             h2d_done.record(copy_stream)
 
     def e2e_step():
         main = torch.cuda.current_stream()
         main.wait_event(h2d_done)
         if graphed is not None:
-            graphed.load_inputs(staging["ex"], staging["ids"], staging["mask"], staging["labels"])   # device -> static buffers
+            graphed.load_inputs(staging["ex"], staging["ids"], staging["mask"], staging["labels"], presence=pres["next"])   # device -> static buffers
             consumed.record(main)
             prefetch()                                           # next batch's H2D overlaps this step's compute
             return step(None, None, None).item()
@@ -290,99 +316,202 @@ def run_ours(args):
     ms_step = ms / args.steps
     ips = world * B / (ms_step / 1e3)
     achieved = g_flop / (g_ms / 1e3) / 1e12
-    gflop_img = TRAIN_GFLOP_PER_IMG if args.resolution == 224 else TRAIN_GFLOP_PER_IMG_480
+    gflop_img = wl["gflop"]
+    traffic, traffic_note = gemm_traffic()
+    act_gb = "activations written and re-read by one step (> 10 GB/GPU) exceed the 126 MB L2"
     out = {
-        "metric": "Prismer-BASE caption-train images/sec", "value": round(ips, 2), "unit": "images/s", "n_gpus": world,
+        "metric": wl["metric"], "value": round(ips, 2), "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"Prismer-BASE caption fine-tune step (fwd+bwd+1 grad all-reduce+AdamW), {args.resolution}x{args.resolution} + 6 expert maps, "
-                               "T=30, freeze_vision, dropout 0.1", "per_gpu_batch": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "l2": ("activations written and re-read by one step (> 10 GB/GPU) exceed the 126 MB L2" if args.compact_inputs
-                                                       else "per-step inputs (1.28 GB/GPU) exceed the 126 MB L2"),
-                   "inputs": "compact: uint8 maps + tables expanded on the GPU (SURVEY 8f N1)" if args.compact_inputs
+        "config": {"workload": wl["workload"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}", "l2": act_gb if compact else "per-step inputs (1.28 GB/GPU) exceed the 126 MB L2; " + act_gb,
+                   "inputs": ("compact expert maps: uint8 label / grey-level maps + <=256-row tables, expanded on the GPU "
+                              "(prismer_b200.data.compact_label_process, a drop-in for dataset/utils.py:117-160; SURVEY 8f N1)") if compact
                              else "reference format: fp32 [B,64,224,224] expert stacks (SURVEY a0)"},
         "e2e": {"value": round(world * B / (ms_e2e / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": h2d + labels_h.numel() * 8,
                 "d2h_bytes_per_step": 4, "note": "pinned H2D of batch i+1 overlaps step i (copy stream); loss.item() every step"},
         "gpu_launches": launches, "cuda_graph": graphed is not None,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": round(achieved, 1), "peak": pk["bf16_tflops_sustained"],
-                     "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4), "traffic": 21438720,
-                     "traffic_note": "dram read+write bytes of ONE ncu --set full launch (M8320 N3072 K768, profiles/ncu_r1_summary.md); "
-                                     "algorithmic operand bytes of that launch: 17.5 MB",
+                     "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_tflops_sustained"], 4), "traffic": traffic,
+                     "traffic_note": traffic_note,
                      "peak_source": pk["source"] + " sustained cuBLAS bf16", "gemm_launches_per_step": len(prof),
                      "gemm_ms_per_step": round(g_ms, 3),
                      "gemm_share_of_step": round(fam.get("gemm_bf16", [0, 0.0])[1] / max(sum(v[1] for v in fam.values()), 1e-9), 3),
-                     "note": "achieved = sum(2MNK)/sum(CUDA-event time) over all 623 GEMM launches of one eager step (half of them are "
-                             "decoder GEMMs with M = 960 rows, launch/latency bound); large shapes run at 850-1000 TFLOP/s "
-                             "(tools/bench_gemm.py)"},
+                     "note": f"achieved = sum(2MNK)/sum(CUDA-event time) over all {len(prof)} GEMM launches of one eager step (about half of "
+                             "them are decoder GEMMs with M = B*T rows, launch/latency bound); encoder-sized shapes run at 850-1200 "
+                             "TFLOP/s (tools/bench_gemm.py)"},
         "step_mfu": {"model_gflop_per_img": gflop_img, "achieved_tflops_per_gpu": round(gflop_img * ips / world / 1e3, 1),
                      "frac_of_peak": round(gflop_img * ips / world / 1e3 / pk["bf16_tflops_sustained"], 4)},
         "host_enqueue_ms_per_step": round(host_ms, 2),
         "entry_point_ms_per_step": kernel_ms,
         "loss": float(loss),
     }
+    if world == 1 and not args.no_secondary and args.config == "base_caption224":
+        # free the training graph(s) before building the captioner (both keep ~10 GB of static activations)
+        del graphed, graphed_keep
+        torch.cuda.empty_cache()
+        if compact:     # the reference's own input format, end to end (1.30 GB of fp32 expert stacks per step through PCIe)
+            out["e2e_reference_inputs"] = e2e_reference_inputs(args, model, opt, ex_h, ids_h, mask_h, labels_h, dev, B)
+        model.eval()
+        cap = run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d, compact, steps=max(5, args.steps // 2), warmup=2)
+        out["secondary"] = {k: cap[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "config", "gpu_launches")}
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_train_baseline(model, sample_batch=2, iters=2, resolution=args.resolution)
+        out["cpu_baseline"] = cpu_train_baseline(model, wl, sample_batch=2, iters=5)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):
-    """Greedy captions/sec (BASELINE config 2): encoder + greedy decode (max_length 20, min_length 8, 4-token prefix)."""
-    import torch.distributed as dist
-    from prismer_b200 import _C, engine, synthetic
-    model.eval()
-    B = args.batch
-    prefix = torch.tensor([[0, 250, 2170, 9]], device=dev).repeat(B, 1)
+def gemm_traffic():
+    """DRAM bytes (read + write) of ONE launch of the dominant GEMM shape, from the committed ncu capture (profiles/ncu_gemm_traffic.json,
+    written by tools/ncu_to_json.py from an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` CSV) -- not a constant in this file."""
+    pth = os.path.join(ROOT, "profiles", "ncu_gemm_traffic.json")
+    if not os.path.exists(pth):
+        return None, "no committed ncu capture (profiles/ncu_gemm_traffic.json)"
+    d = json.load(open(pth))
+    return d["dram_bytes_per_launch"], d["note"]
 
-    from prismer_b200 import generation
-    graphed = None if args.eager else generation.GraphedCaptioner(model, ex_d, prefix, max_length=20, min_length=8)
+
+def e2e_reference_inputs(args, model, opt, ex_h, ids_h, mask_h, labels_h, dev, B):
+    """Secondary end-to-end number with the REFERENCE's input format (fp32 [B,64,224,224] stacks) for the same batch content."""
+    from prismer_b200 import engine, synthetic
+    model.train()
+    ex_f = pin(synthetic.expand_compact_on_host(ex_h))
+    stage = {"ex": synthetic.experts_to(ex_f, dev), "ids": ids_h.to(dev), "mask": mask_h.to(dev), "labels": labels_h.to(dev)}
+    graphed = engine.GraphedTrainStep(model, stage["ex"], stage["ids"], stage["mask"], stage["labels"])
+    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_done, consumed = torch.cuda.Event(), torch.cuda.Event()
+    pres = {"next": None}
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed)
+            engine.copy_experts_(stage["ex"], ex_f, non_blocking=True)
+            stage["ids"].copy_(ids_h, non_blocking=True); stage["mask"].copy_(mask_h, non_blocking=True)
+            stage["labels"].copy_(labels_h, non_blocking=True)
+            pres["next"] = engine.InstancePresence(dev).request(engine.instance_map(stage["ex"]["obj_detection"]), copy_stream)
+            h2d_done.record(copy_stream)
+
+    def one():
+        main = torch.cuda.current_stream()
+        main.wait_event(h2d_done)
+        graphed.load_inputs(stage["ex"], stage["ids"], stage["mask"], stage["labels"], presence=pres["next"])
+        consumed.record(main)
+        prefetch()
+        loss = graphed(None)
+        opt.step()
+        return loss.item()
+
+    consumed.record(torch.cuda.current_stream())
+    prefetch()
+    for _ in range(2):
+        one()
+    n = max(3, args.steps // 4)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        one()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    del graphed
+    torch.cuda.empty_cache()
+    return {"value": round(B / (ms / 1e3), 2), "unit": "images/s", "h2d_bytes_per_step": nbytes(ex_f) + 3 * ids_h.numel() * 8,
+            "d2h_bytes_per_step": 4, "steps": n, "inputs": "reference format: fp32 [B,64,224,224] expert stacks (SURVEY a0)"}
+
+
+def decode_bytes(model, B, S, T0, max_length):
+    """Algorithmic HBM bytes of the KV-cached greedy decode of one batch: per decoder pass every body weight is
+    streamed once (bf16), plus the projected visual K/V of the batch (B x S x H x 2 per layer; 307 MB at BASE -- larger than L2) and the
+    self-attention caches; the tied LM head (V x H) only on the passes that produce logits."""
+    dec = model.text_decoder
+    cfg = dec.config
+    Hd, L = cfg.hidden_size, len(dec.roberta.encoder.layer)
+    head = dec.roberta.embeddings.word_embeddings.weight.numel() + sum(p.numel() for n, p in dec.lm_head.named_parameters() if "decoder" not in n)
+    xkv_w = sum(p.numel() for l in dec.roberta.encoder.layer for p in (l[1].self.key.weight, l[1].self.value.weight))   # used once per call
+    body = sum(p.numel() for p in dec.roberta.encoder.parameters()) - xkv_w
+    passes, head_passes = max_length - 1, max_length - T0
+    cross = L * B * S * Hd * 2
+    return 2 * (passes * (body + cross) + head_passes * head)
+
+
+def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d, compact, steps=None, warmup=None):
+    """Greedy captions/sec (BASELINE config 2): encoder + KV-cached greedy decode (max_length 20, min_length 8, 4-token prefix) as ONE CUDA
+    graph per batch.  Returns the JSON dict (rank 0) -- the caller prints it (``--mode caption``) or embeds it as ``secondary``."""
+    import torch.distributed as dist
+    from prismer_b200 import _C, engine, generation, synthetic
+    model.eval()
+    steps = steps or args.steps
+    warmup = warmup if warmup is not None else args.warmup
+    B = args.batch or CONFIGS[args.config]["batch"]
+    T0, max_length = 4, 20
+    prefix = torch.tensor([[0, 250, 2170, 9]], device=dev).repeat(B, 1)
+    graphed = None if args.eager else generation.GraphedCaptioner(model, ex_d, prefix, max_length=max_length, min_length=8)
 
     def cap(ex):
         with torch.no_grad():
             if graphed is not None:
-                if ex is not ex_d:
-                    graphed.load_inputs(ex)
                 return graphed()
-            if ex is not ex_d:
-                ex = synthetic.experts_to(ex, dev, non_blocking=True)
             enc = model.expert_encoder(ex).transpose(0, 1)
-            return model.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=20, min_length=8)
+            return model.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=max_length, min_length=8)
 
-    for _ in range(args.warmup):
+    c0 = _C.CALLS
+    cap(ex_d)
+    launches = _C.CALLS - c0 if graphed is None else graphed.launches
+    for _ in range(warmup):
         cap(ex_d)
     torch.cuda.synchronize()
-    c0 = _C.CALLS
     sampler = ClockSampler(dev.index or 0)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = cap(ex_d)
     e1.record(); torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = e0.elapsed_time(e1) / steps
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # encoder alone (its own CUDA graph on the same static inputs): decode time = batch time - encoder time
+    enc_ms = None
+    if graphed is not None:
+        g2 = torch.cuda.CUDAGraph()
+        with torch.no_grad():
+            engine.encoder_forward(model.expert_encoder, graphed.experts, save=False, inst_table=graphed.table)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g2):
+                engine.encoder_forward(model.expert_encoder, graphed.experts, save=False, inst_table=graphed.table)
+        for _ in range(2):
+            g2.replay()
+        e0.record()
+        for _ in range(steps):
+            g2.replay()
+        e1.record(); torch.cuda.synchronize()
+        enc_ms = e0.elapsed_time(e1) / steps
+        del g2
     # e2e: pinned-host inputs every batch (H2D of batch i+1 on a copy stream overlaps batch i), ids read back to the host
     copy_stream = torch.cuda.Stream(device=dev)
     staging = synthetic.experts_to(ex_h, dev)
     h2d_done, consumed = torch.cuda.Event(), torch.cuda.Event()
+    has_inst = "obj_detection" in staging
+    pres = {"next": None}
 
     def prefetch():
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed)
             engine.copy_experts_(staging, ex_h, non_blocking=True)
+            if has_inst:
+                pres["next"] = engine.InstancePresence(dev).request(engine.instance_map(staging["obj_detection"]), copy_stream)
             h2d_done.record(copy_stream)
 
     def e2e_cap():
         main = torch.cuda.current_stream()
         main.wait_event(h2d_done)
         if graphed is not None:
-            graphed.load_inputs(staging)
+            graphed.load_inputs(staging, presence=pres["next"])
             consumed.record(main)
             prefetch()
             return graphed().cpu()
@@ -394,68 +523,92 @@ def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d):
     consumed.record(torch.cuda.current_stream())
     prefetch()
     e2e_cap()
-    n2 = max(3, args.steps // 2)
+    n2 = max(3, steps // 2)
     e0.record()
     for _ in range(n2):
         o = e2e_cap()
     e1.record(); torch.cuda.synchronize()
     ms2 = e0.elapsed_time(e1) / n2
-    if rank == 0:
-        print(json.dumps({"metric": "Prismer-BASE greedy captions/sec", "value": round(world * B / (float(t) / 1e3), 2), "unit": "captions/s",
-                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(float(t), 3),
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                          "config": {"workload": "Prismer-BASE caption inference, 224x224 + 6 expert maps, greedy max_length 20",
-                                     "per_gpu_batch": B, "l2": "per-batch inputs (1.28 GB/GPU) exceed the 126 MB L2"},
-                          "e2e": {"value": round(world * B / (ms2 / 1e3), 2), "unit": "captions/s", "h2d_bytes_per_step": h2d,
-                                  "d2h_bytes_per_step": int(o.numel() * 8)},
-                          "gpu_launches": (_C.CALLS - c0) // args.steps if graphed is None else "one cudaGraphLaunch (~3400 kernels)",
-                          "cuda_graph": graphed is not None, "clocks": clocks}), flush=True)
+    if rank != 0:
+        return None
+    pk = peaks()
+    S = graphed.S if graphed is not None else 260
+    nbytes_dec = decode_bytes(model, B, S, T0, max_length)
+    dec_ms = float(t) - enc_ms if enc_ms is not None else None
+    roof = None
+    if dec_ms is not None and dec_ms > 0:
+        gbs = nbytes_dec / (dec_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "KV-cached decode (skinny_linear / decode_attn, csrc/decode.cu), whole decode of one batch",
+                "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": None,
+                "algorithmic_bytes_per_batch": nbytes_dec, "decode_ms_per_batch": round(dec_ms, 3), "encoder_ms_per_batch": round(enc_ms, 3),
+                "encoder_tflops": round(85.2 * B / enc_ms, 1), "peak_source": pk["source"] + " copy bandwidth",
+                "note": "bytes = 19 decoder passes x (body weights + projected visual K/V of the batch) + 16 LM-head passes (SURVEY 8d config 2); "
+                        "decode time = graphed batch time - graphed encoder-only time"}
+    return {"metric": "Prismer-BASE greedy captions/sec", "value": round(world * B / (float(t) / 1e3), 2), "unit": "captions/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(float(t), 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Prismer-BASE caption inference, 224x224 + 6 expert maps, greedy max_length 20 (KV-cached decode)",
+                       "per_gpu_batch": B, "inputs": "compact expert maps" if compact else "reference format fp32 expert stacks",
+                       "l2": "per-batch decode traffic (weights + visual K/V: ~0.65 GB per token step) exceeds the 126 MB L2"},
+            "e2e": {"value": round(world * B / (ms2 / 1e3), 2), "unit": "captions/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(o.numel() * 8)},
+            "gpu_launches": launches, "cuda_graph": graphed is not None, "clocks": clocks, "roofline": roof}
 
 
 # ----------------------------------------------------------------------------------------------------------- CPU arms
-def cpu_train_baseline(model, sample_batch=2, iters=2, threads=None, resolution=224):
-    """The reference's CPU PyTorch path (oracle port: same modules' math, fp32, eager) on a bounded sample of the workload."""
+def cpu_train_baseline(model, wl, sample_batch=2, iters=5, warmup=1, threads=None):
+    """The reference's CPU PyTorch path (oracle port: same modules' math, fp32, eager) on a bounded sample of the workload:
+    ``warmup`` untimed + ``iters`` timed fwd+bwd steps of batch ``sample_batch``; value = images / total timed seconds."""
     from oracle import prismer_oracle as O
     # all the host threads eager PyTorch can use productively: beyond ~32 threads the small per-op work of this path is
     # oversubscribed (measured on the 128-core GPU host: 128 threads -> 12.2 s/step, 8 threads -> 1.4 s/step for batch 2)
     threads = threads or min(os.cpu_count() or 1, 32)
     torch.set_num_threads(threads)
     sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
-    ex, ids, mask = build_inputs(sample_batch, 7, resolution=resolution)
+    ex, ids, mask = build_inputs(sample_batch, 7, T=wl["T"], resolution=wl["res"])
     train_keys = {n for n, p in model.named_parameters() if p.requires_grad}
     for k, v in sd.items():
         if k in train_keys:
             v.requires_grad_(True)
+    patch, heads = (16, 12) if wl["model"] == "prismer_base" else (14, 16)
     times = []
-    for i in range(iters + 1):
+    for i in range(warmup + iters):
         t0 = time.time()
-        loss, _, _ = O.caption_train_loss(ex, ids, mask, 4, sd, 16, 12, training_bn=True)
+        loss, _, _ = O.caption_train_loss(ex, ids, mask, 4, sd, patch, heads, training_bn=True)
         loss.backward()
         for v in sd.values():
             v.grad = None
         times.append(time.time() - t0)
-    t = statistics.median(times[1:])
-    return {"value": round(sample_batch / t, 3), "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"{iters} fwd+bwd steps of batch {sample_batch} (same BASE config, fp32 eager PyTorch on the host), {t:.1f} s/step"}
+    timed = times[warmup:]
+    total = sum(timed)
+    return {"value": round(sample_batch * len(timed) / total, 3), "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{len(timed)} timed fwd+bwd steps of batch {sample_batch} after {warmup} warm-up ({wl['model']}, same config, fp32 eager "
+                      f"PyTorch on the host), {total / len(timed):.2f} s/step (min {min(timed):.2f}, max {max(timed):.2f})",
+            "ms_per_step": round(1e3 * total / len(timed), 1), "steps": len(timed), "warmup": warmup}
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port), rank 0 only.  It RUNS what it prints: `steps` timed and
+    `warmup` untimed steps, each a fwd+bwd of a 2-image batch of the same workload (bounded so the run ends within minutes)."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     from prismer_b200.prismer_caption import PrismerCaption
+    wl = CONFIGS[args.config]
     torch.manual_seed(0)
-    cfg = {"experts": EXPERTS, "prismer_model": "prismer_base", "image_resolution": args.resolution, "freeze": "freeze_vision"}
+    cfg = {"experts": EXPERTS, "prismer_model": wl["model"], "image_resolution": wl["res"], "freeze": wl["freeze"]}
     model = PrismerCaption(cfg)          # parameter container only (CPU); the arithmetic below is the oracle port
     sb = 2
-    t0 = time.time()
-    base = cpu_train_baseline(model, sample_batch=sb, iters=max(1, min(args.steps, 3)), resolution=args.resolution)
+    steps, warmup = max(1, min(args.steps, 30)), max(0, min(args.warmup, 5))
+    base = cpu_train_baseline(model, wl, sample_batch=sb, iters=steps, warmup=warmup)
     ips = base["value"]
-    print(json.dumps({"impl": "reference", "metric": "Prismer-BASE caption-train images/sec", "value": ips, "unit": "images/s",
-                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sb / ips, 1),
+    print(json.dumps({"impl": "reference", "metric": wl["metric"], "value": ips, "unit": "images/s",
+                      "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": base["ms_per_step"],
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "Prismer-BASE caption fine-tune step on the host CPU (reference modules' math, eager fp32)",
-                                 "per_gpu_batch": sb},
+                      "config": {"workload": wl["workload"], "name": args.config, "per_gpu_batch": args.batch or wl["batch"],
+                                 "global_batch": (args.batch or wl["batch"]) * max(1, world), "parallelism": f"dp{max(1, world)}",
+                                 "sample": f"each timed step is a fwd+bwd of a {sb}-image sample of this workload on the host CPU (reference "
+                                           "modules' math, eager fp32); value = images / timed seconds"},
                       "cpu_baseline": base,
                       "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}), flush=True)
@@ -468,15 +621,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "caption"])
-    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--config", default="base_caption224", choices=sorted(CONFIGS),
+                    help="workload: base_caption224 = BASELINE.json's metric configuration (default); large_* = BASELINE configs 4 / 5")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = the configuration's own)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the greedy-captions/s and reference-input-format secondary measurements")
+    ap.add_argument("--reference-inputs", action="store_true",
+                    help="feed the reference's fp32 [B,64,224,224] expert stacks instead of the compact uint8 maps + tables (default)")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph: launch every kernel of the step from Python")
-    ap.add_argument("--overlap-optimizer", action="store_true",
-                    help="experiment: two-graph step; AdamW of the decoder slice runs on a side stream during the encoder backward")
-    ap.add_argument("--resolution", type=int, default=224, choices=[224, 480],
-                    help="rgb resolution: 224 = BASELINE.json's configuration (default), 480 = the reference's configs/caption.yaml (secondary row)")
-    ap.add_argument("--compact-inputs", action="store_true",
-                    help="feed uint8 label maps + tables (prismer_b200.data) instead of the reference's fp32 expert stacks")
+    ap.add_argument("--compact-inputs", action="store_true", help="(default since round 2; kept for old command lines)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -95,19 +95,24 @@ class GraphedCaptioner:
         self.ids = torch.full((prefix_ids.shape[0], max_length), dec.config.pad_token_id, dtype=torch.int64, device=dev)
         self.has_inst = "obj_detection" in self.experts
         self.table = torch.zeros(256, dtype=torch.int32, device=dev) if self.has_inst else None
+        self.presence = engine.InstancePresence(dev).request(engine.instance_map(self.experts["obj_detection"])) if self.has_inst else None
 
         def run():
             self.ids.fill_(dec.config.pad_token_id)
             self.ids[:, :self.T0] = self.prefix
             out, S, B, _ = engine.encoder_forward(vit, self.experts, save=False, inst_table=self.table)
+            self.S = S
             enc = out.view(S, B, -1).transpose(0, 1)
             _greedy_loop(dec, self.ids, self.T0, enc, max_length, min_length, early_exit=False)
 
+        from . import _C
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s), torch.no_grad():
             self._draw_table()
+            c0 = _C.CALLS
             run()
+            self.launches = _C.CALLS - c0          # C-ABI calls (>= 1 kernel each) captured in the graph
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -115,11 +120,14 @@ class GraphedCaptioner:
             run()
 
     def _draw_table(self):
-        if self.has_inst:
-            self.table.copy_(engine._instance_table(engine.instance_map(self.experts["obj_detection"])), non_blocking=True)
+        if self.has_inst:       # flags were computed when the inputs were loaded (engine.InstancePresence): no blocking D2H here
+            self.table.copy_(self.presence.table())     # 1 KiB from pageable memory: staged by the driver at call time, stream-ordered
 
-    def load_inputs(self, experts, non_blocking=True):
+    def load_inputs(self, experts, non_blocking=True, presence=None):
         engine.copy_experts_(self.experts, experts, non_blocking)
+        if self.has_inst:
+            self.presence = presence if presence is not None else engine.InstancePresence(self.store.device).request(
+                engine.instance_map(self.experts["obj_detection"]))
 
     def __call__(self) -> torch.Tensor:
         """Replay on the current static inputs; returns the [B, max_length] id buffer (use ``trim_finished`` for HF's length)."""

@@ -239,8 +239,8 @@ def assemble_tokens(src, pos16, dst, dst_bs, dst_rs, B, n_tok, D, gh, gw, inst=N
                                            dst_bs, dst_rs, B, n_tok, D, gh, gw, Hi, Wi, _stream()), "assemble_tokens")
 
 
-def id_presence(inst):
-    flags = torch.empty(256, dtype=torch.int32, device=inst.device)
+def id_presence(inst, out=None):
+    flags = torch.empty(256, dtype=torch.int32, device=inst.device) if out is None else out
     check(_C.lib().prismer_id_presence(inst.data_ptr(), inst.numel(), flags.data_ptr(), _stream()), "id_presence")
     return flags
 

@@ -12,7 +12,8 @@ KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "
         "config", "e2e", "gpu_launches", "clocks"}
 
 
-@pytest.mark.parametrize("mode", [["train"], ["caption", "compact"], ["train", "compact", "overlap"]], ids=lambda m: "+".join(m))
+@pytest.mark.parametrize("mode", [["train"], ["caption"], ["train", "reference", "nosecondary"], ["train", "large_pretrain224", "nosecondary"]],
+                         ids=lambda m: "+".join(m))
 def test_bench_host_logic(mode):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_dryrun.py")] + mode, cwd=ROOT, capture_output=True, text=True,
                        timeout=600)
@@ -23,5 +24,9 @@ def test_bench_host_logic(mode):
     assert set(out["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and out["e2e"]["h2d_bytes_per_step"] > 0
     assert "workload" in out["config"] and out["n_gpus"] == 1
     if mode[0] == "train":
-        assert out["metric"] == "Prismer-BASE caption-train images/sec" and {"roofline", "step_mfu"} <= set(out)
+        want = "Prismer-LARGE pretrain images/sec" if "large_pretrain224" in mode else "Prismer-BASE caption-train images/sec"
+        assert out["metric"] == want and {"roofline", "step_mfu"} <= set(out)
+        if "nosecondary" not in mode:          # the driver-run line carries greedy captions/s (+ decode roofline) and the fp32-input e2e
+            assert out["secondary"]["unit"] == "captions/s" and out["secondary"]["roofline"]["bound"] == "hbm"
+            assert out["e2e_reference_inputs"]["h2d_bytes_per_step"] > 10 * out["e2e"]["h2d_bytes_per_step"]
         assert set(out["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}

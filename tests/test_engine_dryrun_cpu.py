@@ -181,6 +181,13 @@ class _FakeStream:
     def __exit__(self, *a): return False
 
 
+class _FakeEvent:
+    def __init__(self, *a, **k): pass
+    def record(self, stream=None): pass
+    def synchronize(self): pass
+    def elapsed_time(self, other): return 1.0
+
+
 class _FakeGraph:
     replays = 0
     def pool(self): return None
@@ -196,6 +203,7 @@ def fake_cuda(monkeypatch):
     monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "CUDAGraph", _FakeGraph)
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
     monkeypatch.setattr(torch.cuda, "graph", lambda g, pool=None: contextlib.nullcontext())
     _FakeGraph.replays = 0
 

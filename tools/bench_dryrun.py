@@ -3,7 +3,7 @@ tests/test_engine_dryrun_cpu.py (arity-checks every C call, computes nothing) an
 `run_ours` flow -- model build, graph capture, timed loop, e2e prefetch loop, roofline / per-entry-point passes, JSON line -- executes.
 Numbers are meaningless; a crash here is a crash on the GPU box.
 
-    python tools/bench_dryrun.py [train|caption] [compact] [overlap]
+    python tools/bench_dryrun.py [train|caption] [reference] [nosecondary] [<config name>]
 """
 import contextlib, sys, json, io, types
 import os
@@ -58,6 +58,7 @@ torch.tensor = lambda *a, **k: orig_full(*a, **{kk: vv for kk, vv in k.items() i
 orig_zeros = torch.zeros
 mode = sys.argv[1] if len(sys.argv) > 1 else 'train'
 args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl='ours', mode=mode, batch=2, no_cpu_baseline=True, eager=False,
-                             compact_inputs='compact' in sys.argv, overlap_optimizer='overlap' in sys.argv, resolution=224)
+                             reference_inputs='reference' in sys.argv, no_secondary='nosecondary' in sys.argv,
+                             config=next((a for a in sys.argv[2:] if a in bench.CONFIGS), 'base_caption224'))
 bench.run_ours(args)
 print('calls:', sum(rec.calls.values()))

@@ -7,7 +7,7 @@ any OTHER exception is a bug in the test or in the host code it drives -- found 
 import contextlib, importlib, inspect, sys, traceback, types, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, pytest
-from tests.test_engine_dryrun_cpu import _Recorder, _FakeStream, _FakeGraph
+from tests.test_engine_dryrun_cpu import _Recorder, _FakeStream, _FakeGraph, _FakeEvent
 from prismer_b200 import _C, ops, engine
 rec = _Recorder()
 _C.lib = lambda: rec
@@ -17,6 +17,8 @@ engine._experts_check = lambda e: None
 engine.SIDE_STREAM = False
 torch.cuda.synchronize = lambda *a, **k: None
 torch.cuda.current_stream = lambda *a, **k: _FakeStream()
+torch.cuda.Event = _FakeEvent
+torch.cuda.stream = lambda s: contextlib.nullcontext()
 torch.cuda.current_device = lambda: 0
 real_device = torch.device
 orig_to = torch.Tensor.to
