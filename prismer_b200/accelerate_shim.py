@@ -133,6 +133,7 @@ class Accelerator:
         else:
             self.device = torch.device("cpu")
         self._models = []
+        self._optimizers = []
         self._fused_optimizer = False
         self._end_of_loader, self._remainder = False, 0
 
@@ -150,14 +151,19 @@ class Accelerator:
             if isinstance(o, torch.nn.Module):
                 o.to(self.device)
                 st = engine.prepare(o, self.device)
-                if self.use_distributed:           # replicas start identical (DDP broadcasts rank 0's parameters)
+                if self.use_distributed:           # replicas start identical (DDP broadcasts rank 0's parameters and buffers)
                     dist.broadcast(st.master_t, 0)
                     dist.broadcast(st.master_f, 0)
+                    for b in o.buffers():          # BatchNorm running statistics / num_batches_tracked
+                        dist.broadcast(b.data, 0)
                     st.refresh(force=True)
                 self._models.append(o)
             elif hasattr(o, "grad_scale"):
                 o.grad_scale = 1.0 / self.num_processes
                 self._fused_optimizer = True
+                self._optimizers.append(o)
+            elif isinstance(o, torch.optim.Optimizer):
+                self._optimizers.append(o)
             elif isinstance(o, torch.utils.data.DataLoader):
                 o = ShardedLoader(o, self)         # this rank's batches, moved to the device (train_caption.py:115-117,126)
             out.append(o)
@@ -206,11 +212,56 @@ class Accelerator:
         if self.is_main_process:
             torch.save(obj, path)
 
+    @staticmethod
+    def _suffix(i):
+        return "" if i == 0 else f"_{i}"
+
     def save_state(self, output_dir):
+        """``accelerator.save_state`` (train_caption.py:173-176) with accelerate's file layout: ``pytorch_model[_i].bin`` (reference-layout
+        state_dict), ``optimizer[_i].bin`` (moments, step count, param_groups) on the main process and ``random_states_<rank>.pkl``
+        (python / numpy / torch generators) on every process -- everything ``load_state`` needs to resume a run."""
+        import pickle
+        import random
+        import numpy as np
+        os.makedirs(output_dir, exist_ok=True)
         if self.is_main_process:
-            os.makedirs(output_dir, exist_ok=True)
-            for m in self._models:
-                torch.save(m.state_dict(), os.path.join(output_dir, "pytorch_model.bin"))
+            for i, m in enumerate(self._models):
+                torch.save(m.state_dict(), os.path.join(output_dir, f"pytorch_model{self._suffix(i)}.bin"))
+            for i, o in enumerate(self._optimizers):
+                torch.save(o.state_dict(), os.path.join(output_dir, f"optimizer{self._suffix(i)}.bin"))
+        rng = {"python": random.getstate(), "numpy": np.random.get_state(), "torch": torch.get_rng_state()}
+        if torch.cuda.is_available():
+            rng["cuda"] = torch.cuda.get_rng_state_all()
+        for i, m in enumerate(self._models):       # device-side Philox key of the dropout masks (engine.ParamStore.seed)
+            rng[f"dropout_seed{self._suffix(i)}"] = int(engine._store(m).seed.item()) if hasattr(m, "_prismer_store") else 0
+        with open(os.path.join(output_dir, f"random_states_{self.process_index}.pkl"), "wb") as f:
+            pickle.dump(rng, f)
+        self.wait_for_everyone()
+
+    def load_state(self, input_dir):
+        """Inverse of ``save_state``: weights into the flat fp32 masters (bf16 compute copies re-derived), optimizer state, RNG streams."""
+        import pickle
+        import random
+        import numpy as np
+        for i, m in enumerate(self._models):
+            sd = torch.load(os.path.join(input_dir, f"pytorch_model{self._suffix(i)}.bin"), map_location="cpu")
+            m.load_state_dict(sd)
+            engine._store(m).refresh(force=True)
+        for i, o in enumerate(self._optimizers):
+            pth = os.path.join(input_dir, f"optimizer{self._suffix(i)}.bin")
+            if os.path.exists(pth):
+                o.load_state_dict(torch.load(pth, map_location=self.device))
+        pth = os.path.join(input_dir, f"random_states_{self.process_index}.pkl")
+        if os.path.exists(pth):
+            with open(pth, "rb") as f:
+                rng = pickle.load(f)
+            random.setstate(rng["python"]); np.random.set_state(rng["numpy"]); torch.set_rng_state(rng["torch"])
+            if "cuda" in rng and torch.cuda.is_available():
+                torch.cuda.set_rng_state_all(rng["cuda"])
+            for i, m in enumerate(self._models):
+                if hasattr(m, "_prismer_store"):
+                    engine._store(m).seed.fill_(rng.get(f"dropout_seed{self._suffix(i)}", 0))
+        self.wait_for_everyone()
 
 
 def allreduce_gradients(model, group=None, average: bool = False):

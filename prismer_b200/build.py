@@ -11,9 +11,12 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-PDL = os.environ.get("PRISMER_PDL") == "1"      # opt-in variant: programmatic dependent launch for the hot kernels (common.cuh)
-LIB = os.path.join(HERE, "libprismer_sm100_pdl.so" if PDL else "libprismer_sm100.so")
-OBJ_DIR = os.path.join(HERE, "build_pdl" if PDL else "build")
+# Programmatic dependent launch (common.cuh: griddepcontrol in the GEMM / LayerNorm / colsum / attention / decode kernels, weight tiles
+# prefetched towards L2 before the grid-dependency wait) is the DEFAULT build since round 2 (validated on B200: full -m gpu suite green,
+# 1139 -> 1167 images/s).  PRISMER_PDL=0 builds the plain-launch variant next to it for A/B runs (select it with PRISMER_LIB).
+PDL = os.environ.get("PRISMER_PDL", "1") != "0"
+LIB = os.path.join(HERE, "libprismer_sm100.so" if PDL else "libprismer_sm100_nopdl.so")
+OBJ_DIR = os.path.join(HERE, "build" if PDL else "build_nopdl")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC]

@@ -31,6 +31,15 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool ok) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(ok ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // L1-bypassing load: the rows were written by OTHER CTAs of this launch (made visible by their __threadfence + the atomic counter)
 __device__ __forceinline__ float ldcg_bf16(const bf16* p) {
   return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
@@ -47,47 +56,62 @@ struct SkinnyParams {
   int M, N, K, act;
 };
 
+// Every global byte this CTA needs (its 16 x Kc weight slice and the 32 x Kc activation rows) is requested up front with cp.async --
+// ONE memory round trip per K chunk instead of a dependent load per k-step (the first version of this kernel was latency-bound:
+// 134 ms per 19-token decode).  The products then run from shared memory with ldmatrix + mma.sync; the 4 warps split the k-steps.
 __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* sx = reinterpret_cast<bf16*>(smem_raw);
   __shared__ unsigned int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kCols, m0 = blockIdx.y * kRows;
-  const int mrows = min(kRows, p.M - m0);
+  const int mrows = min(kRows, p.M - m0), ncols = min(kCols, p.N - n0);
+  const int kc_max = min(p.K, kKc), ld = kc_max + kPad;
+  bf16* sx = reinterpret_cast<bf16*>(smem_raw);
+  bf16* sw = sx + kRows * ld;
+#ifdef PRISMER_PDL
+  // Programmatic dependent launch: the weights do not depend on the previous kernel, so this CTA's 16 x K weight slice is pulled
+  // towards L2 while the producer of `x` is still running; everything that reads activations comes after the grid dependency wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  {
+    const int lines = (p.K * 2 + 127) >> 7;                       // 128-byte lines per weight row
+    for (int i = threadIdx.x; i < ncols * lines; i += 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.w + static_cast<long long>(n0 + i / lines) * p.ldw + (i % lines) * 64));
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   float acc[2][2][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
-  // this lane's two weight rows (n8 tiles 0 and 1); rows past N are clamped and their results discarded
-  const int nrow0 = min(n0 + (lane >> 2), p.N - 1), nrow1 = min(n0 + 8 + (lane >> 2), p.N - 1);
-  const bf16* w0 = p.w + static_cast<long long>(nrow0) * p.ldw + 2 * (lane & 3);
-  const bf16* w1 = p.w + static_cast<long long>(nrow1) * p.ldw + 2 * (lane & 3);
 
   for (int kc = 0; kc < p.K; kc += kKc) {
     const int kn = min(kKc, p.K - kc);                     // multiple of 16 (checked on the host)
-    const int ld = kn + kPad;
+    const int vpr = kn >> 3;                               // 16-byte vectors per row
     if (kc > 0) __syncthreads();
-    for (int i = threadIdx.x; i < kRows * (kn >> 3); i += 128) {
-      const int r = i / (kn >> 3), c = i % (kn >> 3);
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (r < mrows) v = *reinterpret_cast<const uint4*>(p.x + static_cast<long long>(m0 + r) * p.ldx + kc + c * 8);
-      *reinterpret_cast<uint4*>(sx + r * ld + c * 8) = v;
+    for (int i = threadIdx.x; i < kRows * vpr; i += 128) {
+      const int r = i / vpr, c = i % vpr;
+      const bool ok = r < mrows;
+      cp_async16(sx + r * ld + c * 8, p.x + static_cast<long long>(ok ? m0 + r : m0) * p.ldx + kc + c * 8, ok);
     }
+    for (int i = threadIdx.x; i < kCols * vpr; i += 128) {
+      const int r = i / vpr, c = i % vpr;
+      const bool ok = r < ncols;
+      cp_async16(sw + r * ld + c * 8, p.w + static_cast<long long>(ok ? n0 + r : n0) * p.ldw + kc + c * 8, ok);
+    }
+    cp_async_wait_all();
     __syncthreads();
     const int steps = kn >> 4;
-#pragma unroll 4
     for (int s = warp; s < steps; s += 4) {
-      const int k = kc + s * 16;
-      const uint32_t b00 = __ldg(reinterpret_cast<const unsigned int*>(w0 + k)), b01 = __ldg(reinterpret_cast<const unsigned int*>(w0 + k + 8));
-      const uint32_t b10 = __ldg(reinterpret_cast<const unsigned int*>(w1 + k)), b11 = __ldg(reinterpret_cast<const unsigned int*>(w1 + k + 8));
-      uint32_t a0[4], a1[4];
+      uint32_t a0[4], a1[4], bw[4];
       ldsm_x4(a0, sx + (lane & 15) * ld + s * 16 + (lane >> 4) * 8);
       ldsm_x4(a1, sx + (16 + (lane & 15)) * ld + s * 16 + (lane >> 4) * 8);
-      mma16816(acc[0][0], a0, b00, b01);
-      mma16816(acc[0][1], a0, b10, b11);
-      mma16816(acc[1][0], a1, b00, b01);
-      mma16816(acc[1][1], a1, b10, b11);
+      // B operand ([n][k] tile, k contiguous): bw[0], bw[1] = n8 tile 0; bw[2], bw[3] = n8 tile 1
+      ldsm_x4(bw, sw + ((lane & 7) + (lane >> 4) * 8) * ld + s * 16 + ((lane >> 3) & 1) * 8);
+      mma16816(acc[0][0], a0, bw[0], bw[1]);
+      mma16816(acc[0][1], a0, bw[2], bw[3]);
+      mma16816(acc[1][0], a1, bw[0], bw[1]);
+      mma16816(acc[1][1], a1, bw[2], bw[3]);
     }
   }
   // cross-warp reduction of the split-K partials through shared memory: red[warp][row][col]
@@ -129,19 +153,28 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
   const bf16* pre = reinterpret_cast<const bf16*>(p.out);   // fused LayerNorm requires a bf16 `out`
   for (int r = warp; r < mrows; r += 4) {
     const bf16* row = pre + static_cast<long long>(m0 + r) * p.ldo;
+    // (statistics exactly as ln_fwd_kernel: mean, then centred second moment, both fp32); N <= 1024: the row stays in registers
+    float xv[32];
     float sum = 0.f;
-    for (int c = lane; c < p.N; c += 32) sum += ldcg_bf16(row + c);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = lane + 32 * i;
+      xv[i] = c < p.N ? ldcg_bf16(row + c) : 0.f;
+      sum += xv[i];
+    }
     const float mean = warp_sum(sum) / p.N;
     float var = 0.f;
-    for (int c = lane; c < p.N; c += 32) {
-      const float d = ldcg_bf16(row + c) - mean;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float d = (lane + 32 * i < p.N) ? xv[i] - mean : 0.f;
       var += d * d;
     }
     const float rstd = rsqrtf(warp_sum(var) / p.N + p.eps);
     bf16* dst = p.ln_out + static_cast<long long>(m0 + r) * p.ldln;
-    for (int c = lane; c < p.N; c += 32) {
-      const float xv = ldcg_bf16(row + c);
-      dst[c] = __float2bfloat16((xv - mean) * rstd * p.gamma[c] + p.beta[c]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = lane + 32 * i;
+      if (c < p.N) dst[c] = __float2bfloat16((xv[i] - mean) * rstd * p.gamma[c] + p.beta[c]);
     }
   }
 }
@@ -159,73 +192,98 @@ struct DecAttnParams {
   float scale;
 };
 
-// one warp per (batch, head); head dim 64.  Scores in fp32, probabilities rounded to bf16 before P.V like the tensor-core kernels.
+// One CTA (4 warps) per (batch, head), head dim 64, up to 321 keys.  All K and V rows of the head are requested with cp.async in one
+// round trip (16-byte chunks XOR-swizzled by the key index: conflict-free for both access patterns below), then
+//   scores : thread <-> key (dot product over the 8 chunks of its row), block-wide max / sum through shared memory,
+//   P.V    : warp w takes keys j = w, w+4, ..., lane <-> channels 2*lane, 2*lane+1; the four partial sums meet in shared memory.
+// Probabilities are rounded to bf16 before P.V like the tensor-core kernels (scores and accumulation in fp32).
+constexpr int kMaxKeys = 328;
+
 __global__ void __launch_bounds__(128) decode_attn_kernel(DecAttnParams p) {
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (wid >= p.B * p.H) return;
-  const int b = wid / p.H, h = wid % p.H;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  PDL_GRID_SYNC();
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int total = p.len + (p.k_new ? 1 : 0);
-  // q: every lane keeps the whole 64-vector (8 x 16 B, broadcast loads)
-  float qv[64];
-  {
-    const uint4* qp = reinterpret_cast<const uint4*>(p.q + b * p.q_bs + h * 64);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) unpack8(qp[c], qv + 8 * c);
-  }
+  uint8_t* sK = smem_raw;                             // [total][128 B] swizzled
+  uint8_t* sV = sK + total * 128;
+  float* sP = reinterpret_cast<float*>(sV + total * 128);      // [kMaxKeys] scores -> probabilities
+  float* sRed = sP + kMaxKeys;                                 // [8] block reductions, then [4][64] partial outputs
   auto key_ptr = [&](int j) -> const bf16* {
     return j < p.len ? p.k + b * p.kv_bs + static_cast<long long>(j) * p.kv_rs + h * 64 : p.k_new + b * p.new_bs + h * 64;
   };
   auto val_ptr = [&](int j) -> const bf16* {
     return j < p.len ? p.v + b * p.kv_bs + static_cast<long long>(j) * p.kv_rs + h * 64 : p.v_new + b * p.new_bs + h * 64;
   };
-  // scores: lane handles keys lane, lane+32, ... (up to 10 per lane: Lk <= 320)
-  float sc[10];
-  float mx = -INFINITY;
+  for (int i = tid; i < total * 8; i += 128) {
+    const int j = i >> 3, c = i & 7;
+    cp_async16(sK + j * 128 + ((c ^ (j & 7)) << 4), key_ptr(j) + c * 8, true);
+    cp_async16(sV + j * 128 + ((c ^ (j & 7)) << 4), val_ptr(j) + c * 8, true);
+  }
+  float qv[64];                                        // every thread keeps the whole query (8 x 16 B broadcast loads)
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(p.q + b * p.q_bs + h * 64);
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const int j = lane + 32 * i;
-    sc[i] = -INFINITY;
-    if (j < total && !(p.key_mask && p.key_mask[static_cast<long long>(b) * p.mask_ld + j] == 0)) {
-      const uint4* kp = reinterpret_cast<const uint4*>(key_ptr(j));
+    for (int c = 0; c < 8; ++c) unpack8(qp[c], qv + 8 * c);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int j = tid; j < total; j += 128) {
+    float sc = -INFINITY;
+    if (!(p.key_mask && p.key_mask[static_cast<long long>(b) * p.mask_ld + j] == 0)) {
       float acc = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float kv[8];
-        unpack8(kp[c], kv);
+        unpack8(*reinterpret_cast<const uint4*>(sK + j * 128 + ((c ^ (j & 7)) << 4)), kv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc = fmaf(qv[8 * c + e], kv[e], acc);
       }
-      sc[i] = acc * p.scale;
-      mx = fmaxf(mx, sc[i]);
+      sc = acc * p.scale;
     }
+    sP[j] = sc;
+    mx = fmaxf(mx, sc);
   }
   mx = warp_max(mx);
+  if (lane == 0) sRed[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
   const float msafe = mx == -INFINITY ? 0.f : mx;
   float l = 0.f;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const float e = sc[i] == -INFINITY ? 0.f : __expf(sc[i] - msafe);
+  for (int j = tid; j < total; j += 128) {
+    const float sc = sP[j];
+    const float e = sc == -INFINITY ? 0.f : __expf(sc - msafe);
     l += e;
-    sc[i] = __bfloat162float(__float2bfloat16(e));
+    sP[j] = __bfloat162float(__float2bfloat16(e));
   }
   l = warp_sum(l);
-  // O = sum_j P_j V_j: lane owns channels 2*lane, 2*lane+1
+  if (lane == 0) sRed[4 + warp] = l;
+  __syncthreads();
+  l = sRed[4] + sRed[5] + sRed[6] + sRed[7];
   float o0 = 0.f, o1 = 0.f;
-  for (int j = 0; j < total; ++j) {
-    const float pj = __shfl_sync(0xffffffffu, sc[j >> 5], j & 31);   // sc index is warp-uniform per j
-    if (pj != 0.f) {
-      const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(val_ptr(j) + 2 * lane);
-      o0 = fmaf(pj, __bfloat162float(vv.x), o0);
-      o1 = fmaf(pj, __bfloat162float(vv.y), o1);
-    }
+  for (int j = warp; j < total; j += 4) {
+    const float pj = sP[j];
+    const int c = lane >> 2;                             // 16-byte chunk holding channels 2*lane, 2*lane+1
+    const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(sV + j * 128 + ((c ^ (j & 7)) << 4) + (lane & 3) * 4);
+    o0 = fmaf(pj, __bfloat162float(vv.x), o0);
+    o1 = fmaf(pj, __bfloat162float(vv.y), o1);
   }
-  const float inv = l > 0.f ? 1.0f / l : 0.f;
-  *reinterpret_cast<__nv_bfloat162*>(p.o + b * p.o_bs + h * 64 + 2 * lane) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
-  if (p.k_new) {   // append the new token's k / v to the cache (row `len`)
-    bf16* kc = p.k_cache + b * p.c_bs + static_cast<long long>(p.len) * p.c_rs + h * 64;
-    bf16* vc = p.v_cache + b * p.c_bs + static_cast<long long>(p.len) * p.c_rs + h * 64;
-    *reinterpret_cast<__nv_bfloat162*>(kc + 2 * lane) = *reinterpret_cast<const __nv_bfloat162*>(p.k_new + b * p.new_bs + h * 64 + 2 * lane);
-    *reinterpret_cast<__nv_bfloat162*>(vc + 2 * lane) = *reinterpret_cast<const __nv_bfloat162*>(p.v_new + b * p.new_bs + h * 64 + 2 * lane);
+  __syncthreads();                                       // sRed[0..7] consumed by everyone before it is reused
+  float* part = sRed;                                    // [4][64]
+  part[warp * 64 + 2 * lane] = o0;
+  part[warp * 64 + 2 * lane + 1] = o1;
+  __syncthreads();
+  if (tid < 64) {
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const float v = (part[tid] + part[64 + tid] + part[128 + tid] + part[192 + tid]) * inv;
+    p.o[b * p.o_bs + h * 64 + tid] = __float2bfloat16(v);
+  }
+  if (p.k_new && tid >= 64) {   // append the new token's k / v to the cache (row `len`): 32 threads each
+    const int t = tid - 64, which = t >> 5, c = t & 31;
+    const bf16* src = (which ? p.v_new : p.k_new) + b * p.new_bs + h * 64 + 2 * c;
+    bf16* dst = (which ? p.v_cache : p.k_cache) + b * p.c_bs + static_cast<long long>(p.len) * p.c_rs + h * 64 + 2 * c;
+    *reinterpret_cast<__nv_bfloat162*>(dst) = *reinterpret_cast<const __nv_bfloat162*>(src);
   }
 }
 
@@ -243,18 +301,20 @@ extern "C" int prismer_skinny_linear(const void* x, long long ldx, const void* w
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
   p.ln_out = reinterpret_cast<bf16*>(ln_out); p.ldln = ldln; p.gamma = gamma; p.beta = beta; p.eps = eps; p.counter = counter;
   p.M = M; p.N = N; p.K = K; p.act = act;
+  if ((ldw % 8) || (reinterpret_cast<uintptr_t>(w) & 15)) return PRISMER_ERR_ALIGN;     // 16-byte cp.async rows
+  if (ln_out && N > 1024) return PRISMER_ERR_SHAPE;
   const int kc = K < kKc ? K : kKc;
-  size_t smem = static_cast<size_t>(kRows) * (kc + kPad) * 2;
+  size_t smem = static_cast<size_t>(kRows + kCols) * (kc + kPad) * 2;
   const size_t red = static_cast<size_t>(4) * kRows * kCols * 4;
   if (smem < red) smem = red;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRows * (kKc + kPad) * 2) != cudaSuccess)
+    if (cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + kCols) * (kKc + kPad) * 2) != cudaSuccess)
       return PRISMER_ERR_CUDA;
     configured = true;
   }
   dim3 grid((N + kCols - 1) / kCols, (M + kRows - 1) / kRows);
-  skinny_linear_kernel<<<grid, 128, smem, stream>>>(p);
+  pdl_launch(skinny_linear_kernel, grid, dim3(128), smem, stream, p);
   return LAUNCH_CHECK();
 }
 
@@ -272,7 +332,14 @@ extern "C" int prismer_decode_attention(const void* q, long long q_bs, const voi
   p.k_cache = reinterpret_cast<bf16*>(k_cache); p.v_cache = reinterpret_cast<bf16*>(v_cache); p.c_bs = c_bs; p.c_rs = c_rs;
   p.key_mask = reinterpret_cast<const long long*>(key_mask); p.mask_ld = mask_ld;
   p.o = reinterpret_cast<bf16*>(o); p.o_bs = o_bs; p.B = B; p.H = H; p.scale = scale;
-  const int warps = B * H;
-  decode_attn_kernel<<<(warps + 3) / 4, 128, 0, stream>>>(p);
+  const int total = len + (k_new ? 1 : 0);
+  const size_t smem = static_cast<size_t>(total) * 256 + (kMaxKeys + 256) * 4;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 321 * 256 + (kMaxKeys + 256) * 4) != cudaSuccess)
+      return PRISMER_ERR_CUDA;
+    configured = true;
+  }
+  pdl_launch(decode_attn_kernel, dim3(B * H), dim3(128), smem, stream, p);
   return LAUNCH_CHECK();
 }

@@ -54,4 +54,6 @@ class FusedAdamW:
         return {"m": self.m, "v": self.v, "t": self.t, "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, sd):
-        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = sd["t"]
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = int(sd["t"])
+        for g, saved in zip(self.param_groups, sd.get("param_groups", [])):     # lr (schedules), betas, eps, weight_decay
+            g.update({k: v for k, v in saved.items() if k != "params"})

@@ -295,3 +295,35 @@ def test_refresh_sees_updates_made_through_the_parameters(dry):
         st.master_t.mul_(1.0)                                                      # flat-buffer writes (broadcast, fused optimizer) still count
     st.refresh()
     assert dry.calls.get("prismer_cast_f32_bf16", 0) > n2
+
+
+def test_accelerator_save_state_load_state_roundtrip(dry, tmp_path):
+    """Checkpoint resume (train_caption.py:96-109,173-176; round-1 VERDICT missing #8): weights, fused-optimizer moments / step / lr, RNG
+    streams and the device-side dropout key survive save_state -> load_state into freshly built objects."""
+    import random
+    from prismer_b200.accelerate_shim import Accelerator
+    from prismer_b200.optim import FusedAdamW
+    acc = Accelerator()
+    m = _tiny(True)
+    opt = FusedAdamW(m, lr=5e-5, weight_decay=0.05)
+    m, opt = acc.prepare(m, opt)
+    opt.m.normal_(); opt.v.uniform_(); opt.t = 7
+    opt.param_groups[0]["lr"] = 1.25e-5
+    engine._store(m).seed.fill_(4321)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.01)
+    random.seed(99); torch.manual_seed(98)
+    acc.save_state(str(tmp_path))
+    want_r, want_t = random.random(), torch.rand(3)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    acc2 = Accelerator()
+    m2 = _tiny(True)
+    opt2 = FusedAdamW(m2, lr=1.0)
+    m2, opt2 = acc2.prepare(m2, opt2)
+    acc2.load_state(str(tmp_path))
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd0[k]), k
+    assert torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v) and opt2.t == 7 and opt2.param_groups[0]["lr"] == 1.25e-5
+    assert int(engine._store(m2).seed.item()) == 4321
+    assert random.random() == want_r and torch.equal(torch.rand(3), want_t)
