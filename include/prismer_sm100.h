@@ -248,34 +248,6 @@ int prismer_expand_labels(const void* labels, const float* table, long long tabl
 int prismer_label_resample(const void* labels, const float* table, long long table_bs, void* out, int B, int C, int Hi, int Wi,
                            int Ho, int Wo, cudaStream_t stream);
 
-/* ---------------------------------------------------------------------------------------------------------
- * EXPERIMENTAL (round-2 candidate; compiled and exported but not on the default path and not yet validated on hardware):
- * attention as batched tcgen05 GEMMs over (batch, head) problems with L2-resident score matrices.
- *   C_i[M,N] = epilogue(alpha * op(A_i) . op(B_i)^T),  X_i = X + bo * X_bs_outer + bi * X_bs_inner (elements)
- *   mode 0: C = alpha*acc;   mode 1 (softmax backward): C = aux * (acc - rowvec[i*rowvec_bs + row]) * alpha;
- *   mode 2 (probabilities from the forward's saved log-sum-exp): C = exp(alpha*acc - rowvec[i*rowvec_bs + row])
- * Replaces (when enabled) the score / value products of nn.MultiheadAttention (vit.py:52-53) and their backward.
- * --------------------------------------------------------------------------------------------------------- */
-typedef struct PrismerBatchedGemmArgs {
-  const void* A; const void* B; void* C;
-  int M, N, K;
-  long long lda, ldb, ldc;
-  int transA, transB;
-  int batch_outer, batch_inner;
-  long long a_bs_outer, a_bs_inner, b_bs_outer, b_bs_inner, c_bs_outer, c_bs_inner;
-  const void* aux; long long ldaux, aux_bs_outer, aux_bs_inner;
-  const float* rowvec; long long rowvec_bs;
-  int mode;
-  float alpha;
-  int force_bn;   /* 0 = pick the N tile (64 / 128 / 256) that pads N least; tuning override otherwise */
-} PrismerBatchedGemmArgs;
-int prismer_gemm_bf16_batched(const PrismerBatchedGemmArgs* args, cudaStream_t stream);
-/* in place row softmax of bf16 scores [rows, ld] over the first Lk columns (padding columns are zeroed). */
-int prismer_softmax_rows(void* s, long long rows, int Lk, int ld, cudaStream_t stream);
-/* delta[(b*H+h)*Lq + q] = sum_d dO*O, tensors addressed as base + b*bs + q*rs + h*d. */
-int prismer_attn_delta(const void* dout, const void* o, long long bs, long long rs, float* delta, int B, int H, int Lq, int d,
-                       cudaStream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

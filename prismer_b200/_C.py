@@ -34,19 +34,6 @@ class GemmArgs(Structure):
     ]
 
 
-class BatchedGemmArgs(Structure):
-    _fields_ = [
-        ("A", c_void_p), ("B", c_void_p), ("C", c_void_p),
-        ("M", c_int), ("N", c_int), ("K", c_int),
-        ("lda", c_longlong), ("ldb", c_longlong), ("ldc", c_longlong),
-        ("transA", c_int), ("transB", c_int), ("batch_outer", c_int), ("batch_inner", c_int),
-        ("a_bs_outer", c_longlong), ("a_bs_inner", c_longlong), ("b_bs_outer", c_longlong), ("b_bs_inner", c_longlong),
-        ("c_bs_outer", c_longlong), ("c_bs_inner", c_longlong),
-        ("aux", c_void_p), ("ldaux", c_longlong), ("aux_bs_outer", c_longlong), ("aux_bs_inner", c_longlong),
-        ("rowvec", c_void_p), ("rowvec_bs", c_longlong), ("mode", c_int), ("alpha", c_float), ("force_bn", c_int),
-    ]
-
-
 _lib = None
 PROFILE = None   # set to a list to record (entry point, start_event, end_event) around every C-ABI call (bench.py / tools)
 
@@ -101,8 +88,6 @@ def _declare(L):
     L.prismer_check_device.restype = c_int
     L.prismer_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
     L.prismer_gemm_bf16.restype = c_int
-    L.prismer_gemm_bf16_batched.argtypes = [POINTER(BatchedGemmArgs), c_void_p]
-    L.prismer_gemm_bf16_batched.restype = c_int
     for fn in ("prismer_attention_fwd", "prismer_attention_bwd"):
         getattr(L, fn).argtypes = [POINTER(AttnArgs), c_void_p]
         getattr(L, fn).restype = c_int

@@ -36,8 +36,6 @@ SIGNATURES = {
     "prismer_conv_weight_unpack_grad": [P, P, I, I, I, I, P],
     "prismer_cast_pad": [P, P, L, I, I, P],
     "prismer_unpad_add": [P, P, L, I, I, P],
-    "prismer_softmax_rows": [P, L, I, I, P],
-    "prismer_attn_delta": [P, P, L, L, P, I, I, I, I, P],
     "prismer_set_attention_path": [I],
     "prismer_skinny_linear": [P, L, P, L, P, P, L, P, L, I, P, L, P, P, F, P, I, I, I, I, P],
     "prismer_decode_attention": [P, L, P, P, L, L, I, P, P, L, P, P, L, L, P, I, P, L, I, I, I, F, P],

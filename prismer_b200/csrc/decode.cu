@@ -40,11 +40,6 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// L1-bypassing load: the rows were written by OTHER CTAs of this launch (made visible by their __threadfence + the atomic counter)
-__device__ __forceinline__ float ldcg_bf16(const bf16* p) {
-  return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
-}
-
 struct SkinnyParams {
   const bf16* x; long long ldx;
   const bf16* w; long long ldw;
@@ -151,30 +146,45 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
   if (!s_last) return;
   __threadfence();
   const bf16* pre = reinterpret_cast<const bf16*>(p.out);   // fused LayerNorm requires a bf16 `out`
-  for (int r = warp; r < mrows; r += 4) {
-    const bf16* row = pre + static_cast<long long>(m0 + r) * p.ldo;
-    // (statistics exactly as ln_fwd_kernel: mean, then centred second moment, both fp32); N <= 1024: the row stays in registers
-    float xv[32];
+  // 4 lanes per row, 8 rows per warp at once, 16-byte L1-bypassing loads (the rows were written by other CTAs): three short passes
+  // (sum, centred second moment, normalise) of independent loads each -- the first version walked the rows one by one with 2-byte
+  // loads and cost 37 us per launch.  Statistics exactly as ln_fwd_kernel: mean, then centred second moment, both fp32.
+  const int nvec = p.N >> 3, part = lane & 3;
+  for (int r = warp * 8 + (lane >> 2); r < kRows; r += 32) {
+    const bool live = r < mrows;
+    const uint4* row = reinterpret_cast<const uint4*>(pre + static_cast<long long>(m0 + (live ? r : 0)) * p.ldo);
     float sum = 0.f;
+    for (int v = part; v < nvec; v += 4) {
+      float f[8];
+      unpack8(__ldcg(row + v), f);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = lane + 32 * i;
-      xv[i] = c < p.N ? ldcg_bf16(row + c) : 0.f;
-      sum += xv[i];
+      for (int e = 0; e < 8; ++e) sum += f[e];
     }
-    const float mean = warp_sum(sum) / p.N;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float mean = sum / p.N;
     float var = 0.f;
+    for (int v = part; v < nvec; v += 4) {
+      float f[8];
+      unpack8(__ldcg(row + v), f);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float d = (lane + 32 * i < p.N) ? xv[i] - mean : 0.f;
-      var += d * d;
+      for (int e = 0; e < 8; ++e) { const float d = f[e] - mean; var += d * d; }
     }
-    const float rstd = rsqrtf(warp_sum(var) / p.N + p.eps);
-    bf16* dst = p.ln_out + static_cast<long long>(m0 + r) * p.ldln;
+    var += __shfl_xor_sync(0xffffffffu, var, 1);
+    var += __shfl_xor_sync(0xffffffffu, var, 2);
+    const float rstd = rsqrtf(var / p.N + p.eps);
+    if (!live) continue;
+    uint4* dst = reinterpret_cast<uint4*>(p.ln_out + static_cast<long long>(m0 + r) * p.ldln);
+    for (int v = part; v < nvec; v += 4) {
+      float f[8];
+      unpack8(__ldcg(row + v), f);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int c = lane + 32 * i;
-      if (c < p.N) dst[c] = __float2bfloat16((xv[i] - mean) * rstd * p.gamma[c] + p.beta[c]);
+      for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * g[e] + bb[e];
+      dst[v] = pack8(f);
     }
   }
 }
@@ -302,7 +312,7 @@ extern "C" int prismer_skinny_linear(const void* x, long long ldx, const void* w
   p.ln_out = reinterpret_cast<bf16*>(ln_out); p.ldln = ldln; p.gamma = gamma; p.beta = beta; p.eps = eps; p.counter = counter;
   p.M = M; p.N = N; p.K = K; p.act = act;
   if ((ldw % 8) || (reinterpret_cast<uintptr_t>(w) & 15)) return PRISMER_ERR_ALIGN;     // 16-byte cp.async rows
-  if (ln_out && N > 1024) return PRISMER_ERR_SHAPE;
+  if (ln_out && ((N % 8) || (ldo % 8) || (ldln % 8))) return PRISMER_ERR_SHAPE;     // 16-byte rows for the fused LayerNorm
   const int kc = K < kKc ? K : kKc;
   size_t smem = static_cast<size_t>(kRows + kCols) * (kc + kPad) * 2;
   const size_t red = static_cast<size_t>(4) * kRows * kCols * 4;

@@ -368,7 +368,8 @@ __global__ void unpad_add_kernel(const float* __restrict__ src, float* __restric
 }  // namespace
 
 extern "C" int prismer_patchify(const float* x, void* out, int B, int Cin, int R, int p, int Kpad, cudaStream_t stream) {
-  if (R % p || Kpad % 8 || Kpad < Cin * p * p) return PRISMER_ERR_SHAPE;
+  // nn.Conv2d(kernel = stride = p, no padding) ignores the R % p trailing pixels (ViT-L/14 at 480 px: 34 x 34 patches of 476 pixels)
+  if (R < p || Kpad % 8 || Kpad < Cin * p * p) return PRISMER_ERR_SHAPE;
   const int g = R / p;
   patchify_kernel<<<blocks_for(static_cast<long long>(B) * g * g * (Kpad / 8), 256), 256, 0, stream>>>(
       x, reinterpret_cast<bf16*>(out), B, Cin, R, p, g, Cin * p * p, Kpad);

@@ -571,75 +571,6 @@ def _pos_grad(vit, dtok_sf, B, n_tok, D, n_slots, slot_stride, interp):
 
 
 # ---------------------------------------------------------------------------------------------------- ViT block
-# EXPERIMENTAL (round-2 candidate, off by default, not yet validated on hardware): self-attention of the ViT blocks as batched
-# tcgen05 GEMMs over (batch, head) with the [B*H, S, S] probabilities kept for the backward (52 MB bf16 per layer at BASE,
-# L2-resident while in use).  Enable with PRISMER_ATTN_UNFUSED=1.
-import os as _os
-
-ATTN_UNFUSED = _os.environ.get("PRISMER_ATTN_UNFUSED") == "1"
-# "bwd": keep the fused flash forward (nothing but the LSE saved) and run only the BACKWARD as batched GEMMs, recomputing the
-# probabilities from the LSE in the epilogue of the score GEMM -- the backward is where the mma.sync kernels lose most
-# (390 us per ViT layer against ~90 us estimated), and no [B*H, S, S] tensor outlives the layer's backward.
-ATTN_UNFUSED_BWD = _os.environ.get("PRISMER_ATTN_UNFUSED") == "bwd"
-
-
-def _unfused_attn_fwd(qkv, o, B, S, H, save):
-    """qkv: [S*B, 3D] seq-first packed projections; o: [S*B, D] output buffer.  Returns P ([B*H, S, Sp] bf16) or None."""
-    D = o.shape[1]
-    d = D // H
-    Sp = (S + 7) // 8 * 8
-    P = torch.empty((B * H, S, Sp), dtype=BF16, device=qkv.device)
-    ld = B * 3 * D
-    qs = (3 * D, d)                                     # (outer = batch, inner = head) strides of the packed projections
-    ps = (H * S * Sp, S * Sp)
-    ops.gemm_batched(qkv, qkv[:, D:], P, S, S, d, lda=ld, ldb=ld, ldc=Sp, batch_outer=B, batch_inner=H, a_bs=qs, b_bs=qs, c_bs=ps,
-                     alpha=d ** -0.5)                   # scores = scale * Q K^T
-    ops.softmax_rows(P.view(B * H * S, Sp), S)
-    ops.gemm_batched(P, qkv[:, 2 * D:], o, S, d, S, lda=Sp, ldb=ld, ldc=B * D, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps,
-                     b_bs=qs, c_bs=(D, d))              # O = P V
-    return P if save else None
-
-
-def _gemm_attn_bwd(do, o, q, k, v, saved, dq, dk, dv, B, H, Lq, Lk):
-    """Attention backward as batched tcgen05 GEMMs over (batch, head) -- no mask, no dropout.  Every tensor is a seq-first 2-D view
-    [L*B, H*d] (rows l*B + b), possibly a column slice of a packed projection buffer (its row stride is taken from the view).
-    ``saved``: the probabilities [B*H, Lq, Lkp] bf16 kept by ``_unfused_attn_fwd``, or the fused forward's LSE [B, H, Lq] fp32, from
-    which they are recomputed in the score GEMM's epilogue: P = exp(scale * Q K^T - lse)."""
-    d = o.shape[1] // H
-    scale = d ** -0.5
-    lay = lambda t: (B * t.stride(0), (t.stride(0), d))            # (leading dimension, (batch stride, head stride)) of a seq-first view
-    (ldq, qs), (ldk, ks), (ldv, vs), (ldo, os_), (lddo, dos) = lay(q), lay(k), lay(v), lay(o), lay(do)
-    (lddq, dqs), (lddk, dks), (lddv, dvs) = lay(dq), lay(dk), lay(dv)
-    if saved.dtype == F32:
-        Lkp = (Lk + 7) // 8 * 8
-        P = torch.empty((B * H, Lq, Lkp), dtype=BF16, device=q.device)
-        ops.gemm_batched(q, k, P, Lq, Lk, d, lda=ldq, ldb=ldk, ldc=Lkp, batch_outer=B, batch_inner=H, a_bs=qs, b_bs=ks,
-                         c_bs=(H * Lq * Lkp, Lq * Lkp), rowvec=saved, rowvec_bs=Lq, mode=2, alpha=scale)
-    else:
-        P = saved
-    Lkp = P.shape[2]
-    ps = (H * Lq * Lkp, Lq * Lkp)
-    delta = ops.attn_delta(do, o, B, H, Lq, d) if (ldo == lddo and os_ == dos) else None
-    assert delta is not None, "dO and O must share their layout"
-    # dV = P^T dO                                                  [Lk, d] = [Lq, Lk]^T [Lq, d]
-    ops.gemm_batched(P, do, dv, Lk, d, Lq, lda=Lkp, ldb=lddo, ldc=lddv, trans_a=True, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps,
-                     b_bs=dos, c_bs=dvs)
-    # dS = P * (dO V^T - delta) * scale   (softmax backward fused into the epilogue)
-    dS = torch.empty_like(P)
-    ops.gemm_batched(do, v, dS, Lq, Lk, d, lda=lddo, ldb=ldv, ldc=Lkp, batch_outer=B, batch_inner=H, a_bs=dos, b_bs=vs, c_bs=ps, aux=P,
-                     ldaux=Lkp, aux_bs=ps, rowvec=delta, rowvec_bs=Lq, mode=1, alpha=scale)
-    # dQ = dS K ; dK = dS^T Q
-    ops.gemm_batched(dS, k, dq, Lq, d, Lk, lda=Lkp, ldb=ldk, ldc=lddq, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps, b_bs=ks, c_bs=dqs)
-    ops.gemm_batched(dS, q, dk, Lk, d, Lq, lda=Lkp, ldb=ldq, ldc=lddk, trans_a=True, trans_b=True, batch_outer=B, batch_inner=H, a_bs=ps,
-                     b_bs=qs, c_bs=dks)
-
-
-def _unfused_attn_bwd(do, qkv, o, P, dqkv, B, S, H):
-    """Self-attention on packed projections [S*B, 3D] (the ViT blocks): see ``_gemm_attn_bwd``."""
-    D = o.shape[1]
-    _gemm_attn_bwd(do, o, qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], P, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, H, S, S)
-
-
 def _vit_block_fwd(blk, adp, x, B, S, save):
     D, H = x.shape[1], blk.n_head
     at = blk.attn
@@ -647,10 +578,7 @@ def _vit_block_fwd(blk, adp, x, B, S, save):
     qkv = gemm(h, at.in_proj_weight._c16, bias=at.in_proj_bias.data)
     q3 = _sf(qkv, S, B)
     o = torch.empty((S * B, D), dtype=BF16, device=x.device)
-    if ATTN_UNFUSED and D // H == 64:
-        lse = _unfused_attn_fwd(qkv, o, B, S, H, save)          # the saved probabilities take the place of the LSE
-    else:
-        _, lse = ops.attention_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], H, need_lse=save, out=_sf(o, S, B))
+    _, lse = ops.attention_fwd(q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], H, need_lse=save, out=_sf(o, S, B))
     x1 = gemm(o, at.out_proj.weight._c16, bias=at.out_proj.bias.data, residual=x)
     h2, mu2, rs2 = _ln(x1, adp.adaptor_ln, save)
     x2, (za, a) = _mlp_fwd(h2, adp.adaptor.down_proj, adp.adaptor.up_proj, "sqrelu", x1, save)
@@ -672,11 +600,8 @@ def _vit_block_bwd(blk, adp, dx3, sv, B, S):
     _lin_grads(dx1, sv.o, at.out_proj)
     dqkv = torch.empty_like(sv.qkv)
     q3, d3 = _sf(sv.qkv, S, B), _sf(dqkv, S, B)
-    if sv.lse is not None and sv.lse.dim() == 3 and (sv.lse.dtype == BF16 or (ATTN_UNFUSED_BWD and D // H == 64)):
-        _unfused_attn_bwd(do, sv.qkv, sv.o, sv.lse, dqkv, B, S, H)             # experimental: saved P, or LSE -> recomputed P
-    else:
-        ops.attention_bwd(_sf(do, S, B), q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], _sf(sv.o, S, B), sv.lse, H,
-                          dq=d3[..., :D], dk=d3[..., D:2 * D], dv=d3[..., 2 * D:])
+    ops.attention_bwd(_sf(do, S, B), q3[..., :D], q3[..., D:2 * D], q3[..., 2 * D:], _sf(sv.o, S, B), sv.lse, H,
+                      dq=d3[..., :D], dk=d3[..., D:2 * D], dv=d3[..., 2 * D:])
     if at.in_proj_weight.requires_grad:
         _wgrad(dqkv, sv.h, at.in_proj_weight._g32)
         _bgrad(dqkv, at.in_proj_bias._g32)
@@ -731,11 +656,8 @@ def _resampler_bwd(res, svs, dlat, xf, B, N):
         dq = torch.empty_like(sv.q)
         dkv = torch.empty_like(sv.kv)
         kv3, dkv3 = _sf(sv.kv, Lr + N, B), _sf(dkv, Lr + N, B)
-        if ATTN_UNFUSED_BWD and (D // H) % 32 == 0:              # experimental: batched tcgen05 GEMMs, P recomputed from the LSE
-            _gemm_attn_bwd(do, sv.o, sv.q, sv.kv[:, :D], sv.kv[:, D:], sv.lse, dq, dkv[:, :D], dkv[:, D:], B, H, Lr, Lr + N)
-        else:
-            ops.attention_bwd(_sf(do, Lr, B), _sf(sv.q, Lr, B), kv3[..., :D], kv3[..., D:], _sf(sv.o, Lr, B), sv.lse, H,
-                              dq=_sf(dq, Lr, B), dk=dkv3[..., :D], dv=dkv3[..., D:])
+        ops.attention_bwd(_sf(do, Lr, B), _sf(sv.q, Lr, B), kv3[..., :D], kv3[..., D:], _sf(sv.o, Lr, B), sv.lse, H,
+                          dq=_sf(dq, Lr, B), dk=dkv3[..., :D], dv=dkv3[..., D:])
         if at.in_proj_weight.requires_grad:
             wg, bg = at.in_proj_weight._g32, at.in_proj_bias._g32
             _wgrad(dq, sv.kvin[:Lr * B], wg[:D]); _bgrad(dq, bg[:D])

@@ -430,37 +430,3 @@ def unpad_add(src2d, dst2d):
 
 
 # ------------------------------------------------------------------------------------------------ EXPERIMENTAL (round-2 candidate)
-def gemm_batched(a_ptr_view, b_ptr_view, c_view, M, N, K, *, lda, ldb, ldc, trans_a=False, trans_b=False, batch_outer=1, batch_inner=1,
-                 a_bs=(0, 0), b_bs=(0, 0), c_bs=(0, 0), aux=None, ldaux=0, aux_bs=(0, 0), rowvec=None, rowvec_bs=0, mode=0, alpha=1.0, force_bn=0):
-    """Batched tcgen05 GEMM over (batch_outer x batch_inner) problems; every tensor argument is a torch tensor whose
-    ``data_ptr()`` is problem (0, 0); ``*_bs = (outer stride, inner stride)`` in elements.  See include/prismer_sm100.h."""
-    a = _C.BatchedGemmArgs()
-    a.A, a.B, a.C = a_ptr_view.data_ptr(), b_ptr_view.data_ptr(), c_view.data_ptr()
-    a.M, a.N, a.K = M, N, K
-    a.lda, a.ldb, a.ldc = lda, ldb, ldc
-    a.transA, a.transB = int(trans_a), int(trans_b)
-    a.batch_outer, a.batch_inner = batch_outer, batch_inner
-    a.a_bs_outer, a.a_bs_inner = a_bs
-    a.b_bs_outer, a.b_bs_inner = b_bs
-    a.c_bs_outer, a.c_bs_inner = c_bs
-    if aux is not None:
-        a.aux, a.ldaux = aux.data_ptr(), ldaux
-        a.aux_bs_outer, a.aux_bs_inner = aux_bs
-    if rowvec is not None:
-        a.rowvec, a.rowvec_bs = rowvec.data_ptr(), rowvec_bs
-    a.mode, a.alpha, a.force_bn = mode, alpha, force_bn
-    check(_C.lib().prismer_gemm_bf16_batched(ctypes.byref(a), _stream()), "gemm_bf16_batched")
-
-
-def softmax_rows(s2d, Lk):
-    rows, ld = s2d.shape
-    check(_C.lib().prismer_softmax_rows(s2d.data_ptr(), rows, Lk, ld, _stream()), "softmax_rows")
-
-
-def attn_delta(dout_sf, o_sf, B, H, Lq, d):
-    """dout / o: seq-first [Lq*B, H*d] rows (l*B + b).  Returns delta fp32 [B*H, Lq]."""
-    delta = torch.empty((B * H, Lq), dtype=F32, device=o_sf.device)
-    W = o_sf.stride(0)                                   # row width of the (possibly packed) buffer both views live in
-    assert dout_sf.stride(0) == W and o_sf.stride(1) == 1 and dout_sf.stride(1) == 1
-    check(_C.lib().prismer_attn_delta(dout_sf.data_ptr(), o_sf.data_ptr(), W, B * W, delta.data_ptr(), B, H, Lq, d, _stream()), "attn_delta")
-    return delta

@@ -13,7 +13,7 @@ from prismer_b200 import _C, _C_decl, engine, ops, synthetic
 from tests.helpers import TINY_DEC, build_model
 
 EXPERTS = synthetic.DEFAULT_EXPERTS
-STRUCT_CALLS = {"prismer_gemm_bf16": 2, "prismer_gemm_bf16_batched": 2, "prismer_attention_fwd": 2,
+STRUCT_CALLS = {"prismer_gemm_bf16": 2, "prismer_attention_fwd": 2,
                 "prismer_attention_bwd": 2}
 
 
@@ -80,18 +80,6 @@ def test_train_step_host_code(dry, compact, train):
     assert dry.calls["prismer_gemm_bf16"] > 100 and dry.calls["prismer_attention_bwd"] > 5
     assert ("prismer_label_resample" in dry.calls) == compact and ("prismer_expand_labels" in dry.calls) == compact
     assert ("prismer_bn_relu_bwd_eval" in dry.calls) == (not train) and ("prismer_bn_relu_bwd" in dry.calls) == train
-
-
-@pytest.mark.parametrize("mode", ["fwd+bwd", "bwd"])
-def test_experimental_attention_paths_host_code(dry, monkeypatch, mode):
-    monkeypatch.setattr(engine, "ATTN_UNFUSED", mode == "fwd+bwd")
-    monkeypatch.setattr(engine, "ATTN_UNFUSED_BWD", mode == "bwd")
-    m = _tiny(True)
-    ex, ids, mask, labels = _batch()
-    random.seed(0)
-    engine.train_loss(m, ex, ids, mask, labels).backward()
-    # per ViT layer: bwd = P (only when recomputed) + dV + dS + dQ + dK; the resampler (d = 32 here) joins in "bwd" mode
-    assert dry.calls["prismer_gemm_bf16_batched"] >= 2 * (4 + (2 if mode == "fwd+bwd" else 1)) and dry.calls["prismer_attn_delta"] >= 2
 
 
 def test_generation_and_rank_host_code(dry):
