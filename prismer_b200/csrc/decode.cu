@@ -49,18 +49,20 @@ struct SkinnyParams {
   bf16* ln_out; long long ldln; const float* gamma; const float* beta; float eps;
   unsigned int* counter;          // [gridDim.y] self-resetting arrival counters (fused LayerNorm only)
   int M, N, K, act;
+  int kc_len;                    // K chunk staged in shared memory per round trip (multiple of 16, <= kKc)
 };
 
 // Every global byte this CTA needs (its 16 x Kc weight slice and the 32 x Kc activation rows) is requested up front with cp.async --
 // ONE memory round trip per K chunk instead of a dependent load per k-step (the first version of this kernel was latency-bound:
 // 134 ms per 19-token decode).  The products then run from shared memory with ldmatrix + mma.sync; the 4 warps split the k-steps.
+template <bool kFuseLN>
 __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ unsigned int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kCols, m0 = blockIdx.y * kRows;
   const int mrows = min(kRows, p.M - m0), ncols = min(kCols, p.N - n0);
-  const int kc_max = min(p.K, kKc), ld = kc_max + kPad;
+  const int kc_max = min(p.K, p.kc_len), ld = kc_max + kPad;
   bf16* sx = reinterpret_cast<bf16*>(smem_raw);
   bf16* sw = sx + kRows * ld;
 #ifdef PRISMER_PDL
@@ -80,8 +82,8 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
 #pragma unroll
     for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
 
-  for (int kc = 0; kc < p.K; kc += kKc) {
-    const int kn = min(kKc, p.K - kc);                     // multiple of 16 (checked on the host)
+  for (int kc = 0; kc < p.K; kc += p.kc_len) {
+    const int kn = min(p.kc_len, p.K - kc);                     // multiple of 16 (checked on the host)
     const int vpr = kn >> 3;                               // 16-byte vectors per row
     if (kc > 0) __syncthreads();
     for (int i = threadIdx.x; i < kRows * vpr; i += 128) {
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
     if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<long long>(m) * p.ldo + n] = v;
     else reinterpret_cast<bf16*>(p.out)[static_cast<long long>(m) * p.ldo + n] = __float2bfloat16(v);
   }
-  if (!p.ln_out) return;
+  if constexpr (!kFuseLN) return;
   // ---- fused LayerNorm: the last CTA of this row group to arrive normalises the (now complete) rows
   __threadfence();
   __syncthreads();
@@ -146,45 +148,60 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
   if (!s_last) return;
   __threadfence();
   const bf16* pre = reinterpret_cast<const bf16*>(p.out);   // fused LayerNorm requires a bf16 `out`
-  // 4 lanes per row, 8 rows per warp at once, 16-byte L1-bypassing loads (the rows were written by other CTAs): three short passes
-  // (sum, centred second moment, normalise) of independent loads each -- the first version walked the rows one by one with 2-byte
-  // loads and cost 37 us per launch.  Statistics exactly as ln_fwd_kernel: mean, then centred second moment, both fp32.
+  // 4 lanes per row, 8 rows per warp at once; each lane pulls its quarter of the row (<= 32 x 16 bytes, L1-bypassing: the rows were
+  // written by other CTAs) into registers with back-to-back independent loads -- ONE L2 round trip -- and the three passes (sum,
+  // centred second moment, normalise) run from registers.  (Walking the row with a load per loop iteration serialised on the
+  // accumulator and cost 18-37 us per launch.)  Statistics exactly as ln_fwd_kernel: mean, then centred second moment, both fp32.
+  constexpr int kMaxV = 32;                                 // N <= 1024 (checked on the host)
   const int nvec = p.N >> 3, part = lane & 3;
   for (int r = warp * 8 + (lane >> 2); r < kRows; r += 32) {
     const bool live = r < mrows;
     const uint4* row = reinterpret_cast<const uint4*>(pre + static_cast<long long>(m0 + (live ? r : 0)) * p.ldo);
-    float sum = 0.f;
-    for (int v = part; v < nvec; v += 4) {
-      float f[8];
-      unpack8(__ldcg(row + v), f);
+    uint4 raw[kMaxV];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sum += f[e];
+    for (int i = 0; i < kMaxV; ++i) {
+      const int v = part + 4 * i;
+      raw[i] = v < nvec ? __ldcg(row + v) : make_uint4(0, 0, 0, 0);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += f[e];               // padding vectors are zero
     }
     sum += __shfl_xor_sync(0xffffffffu, sum, 1);
     sum += __shfl_xor_sync(0xffffffffu, sum, 2);
     const float mean = sum / p.N;
     float var = 0.f;
-    for (int v = part; v < nvec; v += 4) {
-      float f[8];
-      unpack8(__ldcg(row + v), f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const float d = f[e] - mean; var += d * d; }
+    for (int i = 0; i < kMaxV; ++i) {
+      if (part + 4 * i < nvec) {
+        float f[8];
+        unpack8(raw[i], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = f[e] - mean; var += d * d; }
+      }
     }
     var += __shfl_xor_sync(0xffffffffu, var, 1);
     var += __shfl_xor_sync(0xffffffffu, var, 2);
     const float rstd = rsqrtf(var / p.N + p.eps);
-    if (!live) continue;
-    uint4* dst = reinterpret_cast<uint4*>(p.ln_out + static_cast<long long>(m0 + r) * p.ldln);
-    for (int v = part; v < nvec; v += 4) {
-      float f[8];
-      unpack8(__ldcg(row + v), f);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8 + 4));
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint4* dst = reinterpret_cast<uint4*>(p.ln_out + static_cast<long long>(m0 + (live ? r : 0)) * p.ldln);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * g[e] + bb[e];
-      dst[v] = pack8(f);
+    for (int i = 0; i < kMaxV; ++i) {
+      const int v = part + 4 * i;
+      if (live && v < nvec) {
+        float f[8];
+        unpack8(raw[i], f);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * g[e] + bb[e];
+        dst[v] = pack8(f);
+      }
     }
   }
 }
@@ -313,18 +330,26 @@ extern "C" int prismer_skinny_linear(const void* x, long long ldx, const void* w
   p.M = M; p.N = N; p.K = K; p.act = act;
   if ((ldw % 8) || (reinterpret_cast<uintptr_t>(w) & 15)) return PRISMER_ERR_ALIGN;     // 16-byte cp.async rows
   if (ln_out && ((N % 8) || (ldo % 8) || (ldln % 8))) return PRISMER_ERR_SHAPE;     // 16-byte rows for the fused LayerNorm
-  const int kc = K < kKc ? K : kKc;
+  if (ln_out && N > 1024) return PRISMER_ERR_SHAPE;
+  // K chunk per shared-memory round trip: the whole K (<= 1024) when the grid fits one wave -- a single memory round trip per CTA --,
+  // 256 when there are many more CTAs than SMs (LM head: 3142 CTAs): 25 KB of shared memory per CTA, 8 CTAs per SM hide each other's latency
+  const long long ctas = static_cast<long long>((N + kCols - 1) / kCols) * ((M + kRows - 1) / kRows);
+  int kc = K < kKc ? K : kKc;
+  if (ctas > 3 * 148 && kc > 256) kc = 256;
+  p.kc_len = kc;
   size_t smem = static_cast<size_t>(kRows + kCols) * (kc + kPad) * 2;
   const size_t red = static_cast<size_t>(4) * kRows * kCols * 4;
   if (smem < red) smem = red;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + kCols) * (kKc + kPad) * 2) != cudaSuccess)
+    if (cudaFuncSetAttribute(skinny_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + kCols) * (kKc + kPad) * 2) != cudaSuccess ||
+        cudaFuncSetAttribute(skinny_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + kCols) * (kKc + kPad) * 2) != cudaSuccess)
       return PRISMER_ERR_CUDA;
     configured = true;
   }
   dim3 grid((N + kCols - 1) / kCols, (M + kRows - 1) / kRows);
-  pdl_launch(skinny_linear_kernel, grid, dim3(128), smem, stream, p);
+  if (ln_out) pdl_launch(skinny_linear_kernel<true>, grid, dim3(128), smem, stream, p);
+  else pdl_launch(skinny_linear_kernel<false>, grid, dim3(128), smem, stream, p);
   return LAUNCH_CHECK();
 }
 

@@ -48,24 +48,30 @@ def decode_attention(q, k, v, kv_bs, kv_rs, length, heads, *, k_new=None, v_new=
     return o
 
 
-class KVDecoder:
-    """Per-call decode state: self-attention K/V caches of every layer (+ output layer), the visual K/V, the prompt mask."""
+DECODE_CHAINS = 4      # independent batch slices decoded concurrently on separate streams (graph branches) by the sync-free loop
+_chain_streams = {}
 
-    def __init__(self, dec, enc, batch: int, max_length: int, prompt_mask=None):
+
+class KVDecoder:
+    """Decode state of one batch slice [lo, hi): self-attention K/V caches of every layer (+ output layer), a view of the visual K/V
+    (projected once per call for the whole batch by ``engine.cross_kv``), the prompt mask."""
+
+    def __init__(self, dec, kv, lo: int, hi: int, max_length: int, prompt_mask=None):
         cfg = dec.config
         self.dec = dec
         self.Hd, self.nh = cfg.hidden_size, cfg.num_attention_heads
         assert self.Hd // self.nh == 64, "decode kernels are written for head dim 64 (roberta-base / roberta-large)"
-        dev = enc.device
+        dev = kv.kv_all.device
+        batch = hi - lo
         self.L = len(dec.roberta.encoder.layer)
-        self.kv = engine.cross_kv(dec, enc)                      # visual K/V of all layers: once per call
-        assert self.kv.B == batch and self.kv.S <= 320
+        self.kv, self.lo = kv, lo
+        assert kv.S <= 320
         self.kc = torch.zeros((self.L + 1, batch, max_length, self.Hd), dtype=BF16, device=dev)
         self.vc = torch.zeros_like(self.kc)
         self.mask = torch.ones((batch, max_length), dtype=torch.int64, device=dev)
         if prompt_mask is not None:
             self.mask[:, :prompt_mask.shape[1]] = prompt_mask.to(torch.int64)
-        self.counter = torch.zeros(((batch + 31) // 32,), dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(((batch + 31) // 32,), dtype=torch.int32, device=dev)      # per slice: the slices run concurrently
         self.B, self.Tmax = batch, max_length
 
     def _self_block(self, layer, li, h, t):
@@ -99,10 +105,11 @@ class KVDecoder:
         encoder = dec.roberta.encoder
         kv = self.kv
         ld = kv.kv_all.stride(0)
+        base = kv.kv_all.data_ptr() + 2 * self.lo * kv.bs * ld                                   # this slice's first batch element
         for li, (layer, cross, adp) in enumerate(encoder.layer):
             h = self._self_block(layer, li, h, t)
             q = skinny_linear(h, cross.self.query.weight._c16, cross.self.query.bias.data)
-            kbase = kv.kv_all.data_ptr() + 2 * (li * 2 * Hd)
+            kbase = base + 2 * (li * 2 * Hd)
             o = decode_attention(q, kbase, kbase + 2 * Hd, kv.bs * ld, kv.rs * ld, kv.S, self.nh)   # visual tokens: no mask (roberta.py:225)
             _, hc = skinny_linear(o, cross.output.dense.weight._c16, cross.output.dense.bias.data, residual=h, ln=cross.output.LayerNorm,
                                   counter=self.counter)
@@ -116,23 +123,15 @@ class KVDecoder:
             return None
         lm = dec.lm_head
         _, xl = skinny_linear(h, lm.dense.weight._c16, lm.dense.bias.data, act="gelu", ln=lm.layer_norm, counter=self.counter)
-        V = cfg.vocab_size
-        Vp = (V + 7) // 8 * 8
-        logits = torch.empty((self.B, Vp), dtype=F32, device=h.device)
-        check(_C.lib().prismer_skinny_linear(xl.data_ptr(), xl.stride(0), emb.word_embeddings.weight._c16.data_ptr(), Hd, lm.bias.data.data_ptr(),
-                                             None, 0, logits.data_ptr(), Vp, 1, None, 0, None, None, 0.0, None, self.B, V, Hd, 0, ops._stream()),
-              "skinny_linear")
-        return logits[:, :V]
+        return skinny_linear(xl, emb.word_embeddings.weight._c16, lm.bias.data, out_dtype=F32)      # tied LM head, fp32 logits [B, V]
 
 
-def greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None, prompt_mask=None):
-    """KV-cached counterpart of ``generation._greedy_loop`` (same contract): the prompt is fed token by token (filling the caches),
-    then one token per step.  With ``early_exit=False`` there is no host synchronisation: capturable in a CUDA graph."""
+def _chain(dec, ids, T0, kv, lo, hi, max_length, min_length, early_exit, steps, prompt_mask):
+    """Greedy loop of the batch slice [lo, hi) (``ids``: that slice of the [B, max_length] id buffer) on the current stream."""
     cfg = dec.config
     eos, pad, V = cfg.eos_token_id, cfg.pad_token_id, cfg.vocab_size
-    B = ids.shape[0]
-    st = KVDecoder(dec, enc, B, max_length, prompt_mask)
-    unfinished = torch.ones(B, dtype=torch.int64, device=ids.device)
+    st = KVDecoder(dec, kv, lo, hi, max_length, prompt_mask)
+    unfinished = torch.ones(hi - lo, dtype=torch.int64, device=ids.device)
     last = None
     for t in range(T0):
         last = st.step(ids[:, :t + 1].contiguous(), need_logits=(t == T0 - 1))
@@ -149,3 +148,32 @@ def greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=Non
             break
         last = st.step(ids[:, :cur].contiguous())
     return cur
+
+
+def greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None, prompt_mask=None, chains=None):
+    """KV-cached counterpart of ``generation._greedy_loop_nocache`` (same contract): the prompt is fed token by token (filling the
+    caches), then one token per step.  With ``early_exit=False`` there is no host synchronisation, so the loop can be captured in a
+    CUDA graph -- and the batch is split into ``DECODE_CHAINS`` slices decoded CONCURRENTLY on separate streams (parallel branches of the
+    graph): every kernel of a decode step is a latency-bound link of a ~135-launch dependent chain, so independent chains overlap almost
+    perfectly until the weight streaming (one pass over the decoder weights per chain and token) reaches the HBM roof."""
+    B = ids.shape[0]
+    kv = engine.cross_kv(dec, enc)                       # visual K/V of all layers and the whole batch: once per call
+    assert kv.B == B
+    n = chains if chains is not None else (1 if (early_exit or steps is not None or B < 2 * DECODE_CHAINS) else DECODE_CHAINS)
+    if n <= 1:
+        return _chain(dec, ids, T0, kv, 0, B, max_length, min_length, early_exit, steps, prompt_mask)
+    main = torch.cuda.current_stream(ids.device)
+    bounds = [(B * c // n, B * (c + 1) // n) for c in range(n)]
+    used = []
+    for c, (lo, hi) in enumerate(bounds):
+        key = (str(ids.device), c)
+        s = _chain_streams.get(key)
+        if s is None:
+            s = _chain_streams[key] = torch.cuda.Stream(device=ids.device)
+        s.wait_stream(main)
+        with torch.cuda.stream(s):
+            _chain(dec, ids[lo:hi], T0, kv, lo, hi, max_length, min_length, False, None, None if prompt_mask is None else prompt_mask[lo:hi])
+        used.append(s)
+    for s in used:
+        main.wait_stream(s)
+    return max_length

@@ -118,3 +118,30 @@ def test_cached_schedule_matches_cacheless_schedule(c):
     print(f"{c['name']}: {n} steps compared, ids asserted at {decisive}/{total} positions, outputs identical: "
           f"{o0.shape == o1.shape and bool((o0 == o1).all())}")
     assert decisive * 2 >= total
+
+
+def test_graphed_captioner_multi_chain_equals_single_chain():
+    """The CUDA-graphed captioner decodes the batch as DECODE_CHAINS concurrent slices (separate streams = parallel graph branches); rows
+    are independent, so its ids must equal the single-chain ``generate`` bit for bit."""
+    import random
+    from prismer_b200 import generation, kv_decode, synthetic
+    from tests.helpers import build_model
+    experts = ["depth", "seg_coco", "obj_detection"]
+    B = 2 * kv_decode.DECODE_CHAINS + 3                      # uneven slices
+    m, _ = build_model(256, 2, 16, 64, experts, TINY_DEC, seed=5)
+    m.eval()
+    ex = synthetic.experts_to(synthetic.synth_experts(B, 64, experts, 64, 9), "cuda")
+    prefix = torch.tensor([[0, 11, 12, 13]], device="cuda").repeat(B, 1)
+    random.seed(1)
+    cap = generation.GraphedCaptioner(m, ex, prefix, max_length=12, min_length=6)
+    random.seed(2)
+    got = cap().clone()
+    random.seed(2)                                           # same instance-embedding draw as the replay above
+    with torch.no_grad():
+        enc = m.expert_encoder(ex).transpose(0, 1)
+        want = m.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=12, min_length=6)
+    torch.cuda.synchronize()
+    got = generation.trim_finished(got, 4, TINY_DEC["eos_token_id"])
+    L = min(got.shape[1], want.shape[1])
+    assert torch.equal(got[:, :L], want[:, :L]), (got, want)
+    assert cap.launches > 100
