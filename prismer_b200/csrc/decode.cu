@@ -136,17 +136,19 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
     else reinterpret_cast<bf16*>(p.out)[static_cast<long long>(m) * p.ldo + n] = __float2bfloat16(v);
   }
   if constexpr (!kFuseLN) return;
-  // ---- fused LayerNorm: the last CTA of this row group to arrive normalises the (now complete) rows
-  __threadfence();
+  // ---- fused LayerNorm: the last CTA of this row group to arrive normalises the (now complete) rows.
+  // Release / acquire through the arrival counter itself (bar.sync orders this CTA's stores before thread 0's atom.acq_rel.gpu, which
+  // releases them; the last arriver's atom acquires everybody's) -- NOT __threadfence(): that is MEMBAR.SC.GPU + CCTL.IVALL, measured at
+  // ~18 us per launch here and it stalled the concurrent decode chains of the other streams as well.
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(p.counter + blockIdx.y, 1u);
+    unsigned int prev;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(p.counter + blockIdx.y) : "memory");
     s_last = (prev == gridDim.x - 1) ? 1u : 0u;
     if (s_last) p.counter[blockIdx.y] = 0;                  // ready for the next launch (stream-ordered)
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
   const bf16* pre = reinterpret_cast<const bf16*>(p.out);   // fused LayerNorm requires a bf16 `out`
   // 4 lanes per row, 8 rows per warp at once; each lane pulls its quarter of the row (<= 32 x 16 bytes, L1-bypassing: the rows were
   // written by other CTAs) into registers with back-to-back independent loads -- ONE L2 round trip -- and the three passes (sum,
