@@ -6,8 +6,8 @@
 //
 //   skinny_linear : y[M,N] = act(x[M,K] . W[N,K]^T + bias) (+ residual);  32 rows x 16 columns per CTA, the 4 warps split K, weights
 //                   go global -> mma B fragments directly (32-byte sectors fully used), x is staged once in shared memory.
-//                   Optional fused post-LayerNorm (roberta.py:139,182): the LAST CTA to finish normalises the completed rows
-//                   (fp32 statistics, eps as given) -> the kernel emits both the pre-LN sum and LN(pre) without a second launch.
+//                   (A fused "last CTA normalises the rows" post-LayerNorm was built and measured: its single-CTA tail cost ~20 us per
+//                   launch against ~3 us for a separate ln_fwd launch on 32 rows, so the LayerNorm stays a kernel of its own.)
 //   decode_attn   : one query per (batch, head) over a K/V cache (self-attention: the new token's k / v are appended to the cache in the
 //                   same kernel) or over the projected visual tokens (cross-attention); one warp per (batch, head).
 #include "common.cuh"
@@ -46,8 +46,6 @@ struct SkinnyParams {
   const float* bias;
   const bf16* residual; long long ldr;
   void* out; long long ldo; int out_fp32;
-  bf16* ln_out; long long ldln; const float* gamma; const float* beta; float eps;
-  unsigned int* counter;          // [gridDim.y] self-resetting arrival counters (fused LayerNorm only)
   int M, N, K, act;
   int kc_len;                    // K chunk staged in shared memory per round trip (multiple of 16, <= kKc)
 };
@@ -55,10 +53,8 @@ struct SkinnyParams {
 // Every global byte this CTA needs (its 16 x Kc weight slice and the 32 x Kc activation rows) is requested up front with cp.async --
 // ONE memory round trip per K chunk instead of a dependent load per k-step (the first version of this kernel was latency-bound:
 // 134 ms per 19-token decode).  The products then run from shared memory with ldmatrix + mma.sync; the 4 warps split the k-steps.
-template <bool kFuseLN>
 __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __shared__ unsigned int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kCols, m0 = blockIdx.y * kRows;
   const int mrows = min(kRows, p.M - m0), ncols = min(kCols, p.N - n0);
@@ -134,77 +130,6 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
     if (p.residual) v += __bfloat162float(p.residual[static_cast<long long>(m) * p.ldr + n]);
     if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<long long>(m) * p.ldo + n] = v;
     else reinterpret_cast<bf16*>(p.out)[static_cast<long long>(m) * p.ldo + n] = __float2bfloat16(v);
-  }
-  if constexpr (!kFuseLN) return;
-  // ---- fused LayerNorm: the last CTA of this row group to arrive normalises the (now complete) rows.
-  // Release / acquire through the arrival counter itself (bar.sync orders this CTA's stores before thread 0's atom.acq_rel.gpu, which
-  // releases them; the last arriver's atom acquires everybody's) -- NOT __threadfence(): that is MEMBAR.SC.GPU + CCTL.IVALL, measured at
-  // ~18 us per launch here and it stalled the concurrent decode chains of the other streams as well.
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int prev;
-    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(p.counter + blockIdx.y) : "memory");
-    s_last = (prev == gridDim.x - 1) ? 1u : 0u;
-    if (s_last) p.counter[blockIdx.y] = 0;                  // ready for the next launch (stream-ordered)
-  }
-  __syncthreads();
-  if (!s_last) return;
-  const bf16* pre = reinterpret_cast<const bf16*>(p.out);   // fused LayerNorm requires a bf16 `out`
-  // 4 lanes per row, 8 rows per warp at once; each lane pulls its quarter of the row (<= 32 x 16 bytes, L1-bypassing: the rows were
-  // written by other CTAs) into registers with back-to-back independent loads -- ONE L2 round trip -- and the three passes (sum,
-  // centred second moment, normalise) run from registers.  (Walking the row with a load per loop iteration serialised on the
-  // accumulator and cost 18-37 us per launch.)  Statistics exactly as ln_fwd_kernel: mean, then centred second moment, both fp32.
-  constexpr int kMaxV = 32;                                 // N <= 1024 (checked on the host)
-  const int nvec = p.N >> 3, part = lane & 3;
-  for (int r = warp * 8 + (lane >> 2); r < kRows; r += 32) {
-    const bool live = r < mrows;
-    const uint4* row = reinterpret_cast<const uint4*>(pre + static_cast<long long>(m0 + (live ? r : 0)) * p.ldo);
-    uint4 raw[kMaxV];
-#pragma unroll
-    for (int i = 0; i < kMaxV; ++i) {
-      const int v = part + 4 * i;
-      raw[i] = v < nvec ? __ldcg(row + v) : make_uint4(0, 0, 0, 0);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxV; ++i) {
-      float f[8];
-      unpack8(raw[i], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sum += f[e];               // padding vectors are zero
-    }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    const float mean = sum / p.N;
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < kMaxV; ++i) {
-      if (part + 4 * i < nvec) {
-        float f[8];
-        unpack8(raw[i], f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { const float d = f[e] - mean; var += d * d; }
-      }
-    }
-    var += __shfl_xor_sync(0xffffffffu, var, 1);
-    var += __shfl_xor_sync(0xffffffffu, var, 2);
-    const float rstd = rsqrtf(var / p.N + p.eps);
-    uint4* dst = reinterpret_cast<uint4*>(p.ln_out + static_cast<long long>(m0 + (live ? r : 0)) * p.ldln);
-#pragma unroll
-    for (int i = 0; i < kMaxV; ++i) {
-      const int v = part + 4 * i;
-      if (live && v < nvec) {
-        float f[8];
-        unpack8(raw[i], f);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + v * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + v * 8 + 4));
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * g[e] + bb[e];
-        dst[v] = pack8(f);
-      }
-    }
   }
 }
 
@@ -319,20 +244,13 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(DecAttnParams p) {
 }  // namespace
 
 extern "C" int prismer_skinny_linear(const void* x, long long ldx, const void* w, long long ldw, const float* bias, const void* residual,
-                                     long long ldr, void* out, long long ldo, int out_fp32, void* ln_out, long long ldln,
-                                     const float* gamma, const float* beta, float eps, unsigned int* counter, int M, int N, int K, int act,
-                                     cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || (K % 16) || (ldx % 8) || (ldw % 2)) return PRISMER_ERR_SHAPE;
-  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 3)) return PRISMER_ERR_ALIGN;
-  if (ln_out && (out_fp32 || !gamma || !beta || !counter)) return PRISMER_ERR_SHAPE;
+                                     long long ldr, void* out, long long ldo, int out_fp32, int M, int N, int K, int act, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (K % 16) || (ldx % 8) || (ldw % 8)) return PRISMER_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return PRISMER_ERR_ALIGN;     // 16-byte cp.async rows
   SkinnyParams p;
   p.x = reinterpret_cast<const bf16*>(x); p.ldx = ldx; p.w = reinterpret_cast<const bf16*>(w); p.ldw = ldw; p.bias = bias;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
-  p.ln_out = reinterpret_cast<bf16*>(ln_out); p.ldln = ldln; p.gamma = gamma; p.beta = beta; p.eps = eps; p.counter = counter;
   p.M = M; p.N = N; p.K = K; p.act = act;
-  if ((ldw % 8) || (reinterpret_cast<uintptr_t>(w) & 15)) return PRISMER_ERR_ALIGN;     // 16-byte cp.async rows
-  if (ln_out && ((N % 8) || (ldo % 8) || (ldln % 8))) return PRISMER_ERR_SHAPE;     // 16-byte rows for the fused LayerNorm
-  if (ln_out && N > 1024) return PRISMER_ERR_SHAPE;
   // K chunk per shared-memory round trip: the whole K (<= 1024) when the grid fits one wave -- a single memory round trip per CTA --,
   // 256 when there are many more CTAs than SMs (LM head: 3142 CTAs): 25 KB of shared memory per CTA, 8 CTAs per SM hide each other's latency
   const long long ctas = static_cast<long long>((N + kCols - 1) / kCols) * ((M + kRows - 1) / kRows);
@@ -344,14 +262,12 @@ extern "C" int prismer_skinny_linear(const void* x, long long ldx, const void* w
   if (smem < red) smem = red;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(skinny_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + kCols) * (kKc + kPad) * 2) != cudaSuccess ||
-        cudaFuncSetAttribute(skinny_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + kCols) * (kKc + kPad) * 2) != cudaSuccess)
+    if (cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + kCols) * (kKc + kPad) * 2) != cudaSuccess)
       return PRISMER_ERR_CUDA;
     configured = true;
   }
   dim3 grid((N + kCols - 1) / kCols, (M + kRows - 1) / kRows);
-  if (ln_out) pdl_launch(skinny_linear_kernel<true>, grid, dim3(128), smem, stream, p);
-  else pdl_launch(skinny_linear_kernel<false>, grid, dim3(128), smem, stream, p);
+  pdl_launch(skinny_linear_kernel, grid, dim3(128), smem, stream, p);
   return LAUNCH_CHECK();
 }
 

@@ -3,8 +3,8 @@ re-forward of the whole prefix (roberta.py:401-406, driven by prismer_caption.py
 
 Same arithmetic as ``engine.decoder_forward`` (eval mode) restricted to the last position: the self-attention keys / values of
 earlier positions come from a per-layer cache, the cross-attention K / V of the visual tokens are projected once per call
-(``engine.cross_kv``).  Every product runs on the decode-time kernels of ``csrc/decode.cu`` (``prismer_skinny_linear`` with the
-post-LayerNorm fused into the producing launch, ``prismer_decode_attention``): ~135 small launches per step instead of ~210
+(``engine.cross_kv``).  Every product runs on the decode-time kernels of ``csrc/decode.cu`` (``prismer_skinny_linear``, ``prismer_decode_attention``, the
+post-LayerNorms as 32-row ``prismer_layernorm_fwd`` launches): ~190 small launches per step instead of ~210
 persistent-GEMM launches over a growing prefix.  Token ids are checked bit-exact against the reference goldens and against the
 cache-less path (tests/test_kv_decode_gpu.py).
 """
@@ -18,19 +18,19 @@ from . import _C, engine, ops
 from .ops import BF16, F32, _p, check
 
 
-def skinny_linear(x, w16, bias=None, *, act=0, residual=None, ln=None, counter=None, out_dtype=BF16):
-    """y = act(x . w16^T + bias) (+ residual) for a handful of rows; with ``ln`` (a LayerNorm module) also returns LN(y)."""
+def skinny_linear(x, w16, bias=None, *, act=0, residual=None, ln=None, out_dtype=BF16):
+    """y = act(x . w16^T + bias) (+ residual) for a handful of rows; with ``ln`` (a LayerNorm module) returns (y, LN(y))."""
     M, K = x.shape
     N = w16.shape[0]
     assert x.dtype == BF16 and w16.dtype == BF16 and x.stride(1) == 1 and w16.stride(1) == 1 and w16.shape[1] == K
     out = torch.empty((M, N), dtype=out_dtype, device=x.device)
-    y = torch.empty((M, N), dtype=BF16, device=x.device) if ln is not None else None
     check(_C.lib().prismer_skinny_linear(
         x.data_ptr(), x.stride(0), w16.data_ptr(), w16.stride(0), _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
-        out.data_ptr(), out.stride(0), int(out_dtype == F32), _p(y), N, _p(ln.weight.data) if ln is not None else None,
-        _p(ln.bias.data) if ln is not None else None, float(ln.eps) if ln is not None else 0.0, _p(counter), M, N, K,
-        ops.ACT.get(act, act), ops._stream()), "skinny_linear")
-    return (out, y) if ln is not None else out
+        out.data_ptr(), out.stride(0), int(out_dtype == F32), M, N, K, ops.ACT.get(act, act), ops._stream()), "skinny_linear")
+    if ln is None:
+        return out
+    y, _, _ = ops.layernorm_fwd(out, ln.weight.data, ln.bias.data, ln.eps, save_stats=False)
+    return out, y
 
 
 def decode_attention(q, k, v, kv_bs, kv_rs, length, heads, *, k_new=None, v_new=None, k_cache=None, v_cache=None, key_mask=None, scale=None):
@@ -71,7 +71,6 @@ class KVDecoder:
         self.mask = torch.ones((batch, max_length), dtype=torch.int64, device=dev)
         if prompt_mask is not None:
             self.mask[:, :prompt_mask.shape[1]] = prompt_mask.to(torch.int64)
-        self.counter = torch.zeros(((batch + 31) // 32,), dtype=torch.int32, device=dev)      # per slice: the slices run concurrently
         self.B, self.Tmax = batch, max_length
 
     def _self_block(self, layer, li, h, t):
@@ -81,14 +80,12 @@ class KVDecoder:
         kc, vc = self.kc[li], self.vc[li]
         o = decode_attention(qkv[:, :Hd], kc, vc, kc.stride(0), kc.stride(1), t, self.nh, k_new=qkv[:, Hd:2 * Hd], v_new=qkv[:, 2 * Hd:],
                              k_cache=kc, v_cache=vc, key_mask=self.mask)
-        _, h1 = skinny_linear(o, at.output.dense.weight._c16, at.output.dense.bias.data, residual=h, ln=at.output.LayerNorm,
-                              counter=self.counter)
+        _, h1 = skinny_linear(o, at.output.dense.weight._c16, at.output.dense.bias.data, residual=h, ln=at.output.LayerNorm)
         return h1
 
     def _mlp_block(self, layer, h):
         f = skinny_linear(h, layer.intermediate.dense.weight._c16, layer.intermediate.dense.bias.data, act="gelu")
-        _, h1 = skinny_linear(f, layer.output.dense.weight._c16, layer.output.dense.bias.data, residual=h, ln=layer.output.LayerNorm,
-                              counter=self.counter)
+        _, h1 = skinny_linear(f, layer.output.dense.weight._c16, layer.output.dense.bias.data, residual=h, ln=layer.output.LayerNorm)
         return h1
 
     def step(self, ids_so_far: torch.Tensor, need_logits: bool = True):
@@ -111,18 +108,16 @@ class KVDecoder:
             q = skinny_linear(h, cross.self.query.weight._c16, cross.self.query.bias.data)
             kbase = base + 2 * (li * 2 * Hd)
             o = decode_attention(q, kbase, kbase + 2 * Hd, kv.bs * ld, kv.rs * ld, kv.S, self.nh)   # visual tokens: no mask (roberta.py:225)
-            _, hc = skinny_linear(o, cross.output.dense.weight._c16, cross.output.dense.bias.data, residual=h, ln=cross.output.LayerNorm,
-                                  counter=self.counter)
+            _, hc = skinny_linear(o, cross.output.dense.weight._c16, cross.output.dense.bias.data, residual=h, ln=cross.output.LayerNorm)
             a = skinny_linear(hc, adp.adaptor.down_proj.weight._c16, adp.adaptor.down_proj.bias.data, act="sqrelu")
-            _, ha = skinny_linear(a, adp.adaptor.up_proj.weight._c16, adp.adaptor.up_proj.bias.data, residual=hc, ln=adp.adaptor_ln,
-                                  counter=self.counter)
+            _, ha = skinny_linear(a, adp.adaptor.up_proj.weight._c16, adp.adaptor.up_proj.bias.data, residual=hc, ln=adp.adaptor_ln)
             h = self._mlp_block(layer, ha)
         h = self._self_block(encoder.output_layer, self.L, h, t)
         h = self._mlp_block(encoder.output_layer, h)
         if not need_logits:
             return None
         lm = dec.lm_head
-        _, xl = skinny_linear(h, lm.dense.weight._c16, lm.dense.bias.data, act="gelu", ln=lm.layer_norm, counter=self.counter)
+        _, xl = skinny_linear(h, lm.dense.weight._c16, lm.dense.bias.data, act="gelu", ln=lm.layer_norm)
         return skinny_linear(xl, emb.word_embeddings.weight._c16, lm.bias.data, out_dtype=F32)      # tied LM head, fp32 logits [B, V]
 
 
