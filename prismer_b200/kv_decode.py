@@ -48,7 +48,9 @@ def decode_attention(q, k, v, kv_bs, kv_rs, length, heads, *, k_new=None, v_new=
     return o
 
 
-DECODE_CHAINS = 4      # independent batch slices decoded concurrently on separate streams (graph branches) by the sync-free loop
+# Independent batch slices decoded concurrently on separate streams (parallel branches of the captured graph).  Measured on B200 at B = 32:
+# 1 chain 30.7 ms per batch, 2 chains 31.8, 4 chains 34.5, 8 chains 58 -- the branches do not overlap usefully, so the default is ONE chain.
+DECODE_CHAINS = 1
 _chain_streams = {}
 
 
@@ -148,13 +150,12 @@ def _chain(dec, ids, T0, kv, lo, hi, max_length, min_length, early_exit, steps, 
 def greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None, prompt_mask=None, chains=None):
     """KV-cached counterpart of ``generation._greedy_loop_nocache`` (same contract): the prompt is fed token by token (filling the
     caches), then one token per step.  With ``early_exit=False`` there is no host synchronisation, so the loop can be captured in a
-    CUDA graph -- and the batch is split into ``DECODE_CHAINS`` slices decoded CONCURRENTLY on separate streams (parallel branches of the
-    graph): every kernel of a decode step is a latency-bound link of a ~135-launch dependent chain, so independent chains overlap almost
-    perfectly until the weight streaming (one pass over the decoder weights per chain and token) reaches the HBM roof."""
+    CUDA graph.  Optionally (``chains`` / ``DECODE_CHAINS`` > 1) the batch is split into slices decoded on separate streams (parallel
+    branches of the graph); measured on B200 this does not pay (see DECODE_CHAINS), so one chain is the default."""
     B = ids.shape[0]
     kv = engine.cross_kv(dec, enc)                       # visual K/V of all layers and the whole batch: once per call
     assert kv.B == B
-    n = chains if chains is not None else (1 if (early_exit or steps is not None or B < 2 * DECODE_CHAINS) else DECODE_CHAINS)
+    n = chains if chains is not None else (1 if (early_exit or steps is not None or B < 2 * DECODE_CHAINS or DECODE_CHAINS <= 1) else DECODE_CHAINS)
     if n <= 1:
         return _chain(dec, ids, T0, kv, 0, B, max_length, min_length, early_exit, steps, prompt_mask)
     main = torch.cuda.current_stream(ids.device)

@@ -119,19 +119,23 @@ def test_cached_schedule_matches_cacheless_schedule(c):
 
 
 def test_graphed_captioner_multi_chain_equals_single_chain():
-    """The CUDA-graphed captioner decodes the batch as DECODE_CHAINS concurrent slices (separate streams = parallel graph branches); rows
-    are independent, so its ids must equal the single-chain ``generate`` bit for bit."""
+    """With DECODE_CHAINS > 1 the CUDA-graphed captioner decodes the batch as concurrent slices (separate streams = parallel graph
+    branches); rows are independent, so its ids must equal the single-chain ``generate`` bit for bit."""
     import random
     from prismer_b200 import generation, kv_decode, synthetic
     from tests.helpers import build_model
     experts = ["depth", "seg_coco", "obj_detection"]
+    kv_decode.DECODE_CHAINS = 4                              # (default is 1: the multi-stream variant is kept, tested, not used)
     B = 2 * kv_decode.DECODE_CHAINS + 3                      # uneven slices
     m, _ = build_model(256, 2, 16, 64, experts, TINY_DEC, seed=5)
     m.eval()
     ex = synthetic.experts_to(synthetic.synth_experts(B, 64, experts, 64, 9), "cuda")
     prefix = torch.tensor([[0, 11, 12, 13]], device="cuda").repeat(B, 1)
     random.seed(1)
-    cap = generation.GraphedCaptioner(m, ex, prefix, max_length=12, min_length=6)
+    try:
+        cap = generation.GraphedCaptioner(m, ex, prefix, max_length=12, min_length=6)
+    finally:
+        kv_decode.DECODE_CHAINS = 1
     random.seed(2)
     got = cap().clone()
     random.seed(2)                                           # same instance-embedding draw as the replay above
