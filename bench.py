@@ -175,8 +175,7 @@ def run_ours(args):
     labels_h = labels_d.cpu().pin_memory()
     graphed = None
     if not args.eager:
-        in_graph = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)) if (world > 1 and args.comm_in_graph) else None
-        graphed = engine.GraphedTrainStep(model, ex_d, ids_d, mask_d, labels_d, overlap=world > 1, comm_in_graph=in_graph)
+        graphed = engine.GraphedTrainStep(model, ex_d, ids_d, mask_d, labels_d, overlap=world > 1)
     comm = (lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)) if world > 1 else None
 
     def step(ex, ids, mask, host_inputs=False):
@@ -630,9 +629,6 @@ def main():
     ap.add_argument("--reference-inputs", action="store_true",
                     help="feed the reference's fp32 [B,64,224,224] expert stacks instead of the compact uint8 maps + tables (default)")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph: launch every kernel of the step from Python")
-    ap.add_argument("--comm-in-graph", action="store_true",
-                    help="multi-GPU: capture the NCCL all-reduces INSIDE the step's CUDA graph (one graph, decoder slice reduced on a side "
-                         "branch during the encoder backward) instead of two graphs with the collectives launched between them")
     ap.add_argument("--compact-inputs", action="store_true", help="(default since round 2; kept for old command lines)")
     args = ap.parse_args()
     if args.impl == "reference":

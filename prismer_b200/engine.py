@@ -1033,18 +1033,14 @@ class GraphedTrainStep:
     and is bumped inside the graph) and the instance-embedding table (vit.py:144-146, host ``random.randint``) is drawn on
     the host before every replay and copied into a static device buffer.  Gradients land in the flat fp32 buffer."""
 
-    def __init__(self, model, experts, input_ids, attention_mask, labels, weights=None, warmup: int = 2, overlap: bool = False,
-                 comm_in_graph=None):
+    def __init__(self, model, experts, input_ids, attention_mask, labels, weights=None, warmup: int = 2, overlap: bool = False):
         """``overlap=True`` captures TWO graphs (forward + decoder backward | encoder backward) so that a data-parallel caller
         can all-reduce the decoder slice of the flat gradient buffer (``store.grad_t[:store.n_train_dec]``, 72 % of the bytes
         for BASE freeze_vision) while the encoder backward runs: ``step(comm)``.
-        ``comm_in_graph(tensor)``: an in-place, stream-ordered all-reduce (e.g. ``lambda t: dist.all_reduce(t)`` on NCCL).  When given, ONE
-        graph is captured WITH the collectives inside: the decoder slice is reduced on a side branch of the graph while the encoder
-        backward runs, the encoder slice at the end -- no graph split, no host round trip between the pieces of a step."""
+        (Capturing the NCCL all-reduces INSIDE one graph was tried in round 2 and hung at replay on 2 GPUs with torch 2.11 / NCCL 2.28;
+        the collectives therefore stay between the two graphs.)"""
         self.model = model
-        self.overlap = overlap and comm_in_graph is None
-        self.comm_captured = comm_in_graph is not None
-        overlap = self.overlap
+        self.overlap = overlap
         st = self.store = _store(model)
         st.refresh()
         dev = st.device
@@ -1066,24 +1062,7 @@ class GraphedTrainStep:
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        if comm_in_graph is not None:
-            comm_in_graph(torch.zeros(8, dtype=F32, device=dev))        # communicator set-up cannot be captured: one eager collective first
-            torch.cuda.synchronize(dev)
-            cs = torch.cuda.Stream(device=dev)
-            # thread_local: the NCCL watchdog thread polls events concurrently, which a "global" capture would treat as a violation
-            with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-                loss, esv, dsv = _forward_train(model, self.experts, self.ids, self.mask, self.labels, self.weights, self.table)
-                denc = _backward_decoder(model, dsv, self.gscale)
-                _side_join(dev)                         # decoder weight gradients are final
-                main = torch.cuda.current_stream(dev)
-                cs.wait_stream(main)
-                with torch.cuda.stream(cs):
-                    comm_in_graph(st.grad_t[:st.n_train_dec])
-                _backward_encoder(model, esv, denc)
-                main.wait_stream(cs)
-                comm_in_graph(st.grad_t[st.n_train_dec:])
-                del esv, dsv, denc
-        elif not overlap:
+        if not overlap:
             with torch.no_grad(), torch.cuda.graph(self.graph):
                 loss, esv, dsv = _forward_train(model, self.experts, self.ids, self.mask, self.labels, self.weights, self.table)
                 _backward_train(model, esv, dsv, self.gscale)
@@ -1149,7 +1128,7 @@ class GraphedTrainStep:
                     h.wait()
             if on_decoder_grads is not None:
                 torch.cuda.current_stream().wait_stream(self._opt_stream)
-        elif comm is not None and not self.comm_captured:
+        elif comm is not None:
             comm(self.store.grad_t).wait()
         return self.loss
 

@@ -315,17 +315,3 @@ def test_accelerator_save_state_load_state_roundtrip(dry, tmp_path):
     assert torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v) and opt2.t == 7 and opt2.param_groups[0]["lr"] == 1.25e-5
     assert int(engine._store(m2).seed.item()) == 4321
     assert random.random() == want_r and torch.equal(torch.rand(3), want_t)
-
-
-def test_graphed_train_step_with_collectives_inside_the_graph_host_code(dry, fake_cuda):
-    """``comm_in_graph``: one graph, the all-reduce of the decoder slice and of the rest are issued during capture (after one eager
-    warm-up collective); replay does not call the eager ``comm`` again."""
-    m = _tiny(True)
-    st = engine._store(m)
-    ex, ids, mask, labels = _batch()
-    seen = []
-    graphed = engine.GraphedTrainStep(m, ex, ids, mask, labels, overlap=True, comm_in_graph=lambda t: seen.append(t.numel()))
-    assert seen == [8, st.n_train_dec, st.grad_t.numel() - st.n_train_dec] and not graphed.overlap and graphed.comm_captured
-    eager = []
-    graphed(lambda t: eager.append(t.numel()))
-    assert eager == [] and _FakeGraph.replays == 1

@@ -58,7 +58,7 @@ torch.tensor = lambda *a, **k: orig_full(*a, **{kk: vv for kk, vv in k.items() i
 orig_zeros = torch.zeros
 mode = sys.argv[1] if len(sys.argv) > 1 else 'train'
 args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl='ours', mode=mode, batch=2, no_cpu_baseline=True, eager=False,
-                             reference_inputs='reference' in sys.argv, comm_in_graph=False, no_secondary='nosecondary' in sys.argv,
+                             reference_inputs='reference' in sys.argv, no_secondary='nosecondary' in sys.argv,
                              config=next((a for a in sys.argv[2:] if a in bench.CONFIGS), 'base_caption224'))
 bench.run_ours(args)
 print('calls:', sum(rec.calls.values()))
