@@ -123,6 +123,10 @@ typedef struct PrismerAttnArgs {
   void* dk; long long dk_bs, dk_rs;
   void* dv; long long dv_bs, dv_rs;
   float* delta;
+  /* forward only: keys / values of batch row b are read from K/V batch b / kv_div (0 or 1 = b).  The k-way candidate pass of
+   * inference='rank' (prismer_caption.py:94-96, prismer_vqa.py:95-97) shares one set of visual K/V per image instead of tile()-ing the
+   * encoder states k times. */
+  int kv_div;
 } PrismerAttnArgs;
 
 int prismer_attention_fwd(const PrismerAttnArgs* args, cudaStream_t stream);

@@ -118,4 +118,5 @@ class AttnArgs(Structure):
         ("dk", c_void_p), ("dk_bs", c_longlong), ("dk_rs", c_longlong),
         ("dv", c_void_p), ("dv_bs", c_longlong), ("dv_rs", c_longlong),
         ("delta", c_void_p),
+        ("kv_div", c_int),
     ]

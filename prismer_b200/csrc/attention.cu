@@ -36,6 +36,7 @@ struct AttnParams {
   bf16* dk; long long dk_bs, dk_rs;
   bf16* dv; long long dv_bs, dv_rs;
   float* delta;               // [B, H, Lq]
+  int kv_div;                 // forward: K/V batch index = b / kv_div (>= 1)
 };
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(AttnParams p) {
   const bf16* qg = p.q + b * p.q_bs + static_cast<long long>(q0) * p.q_rs + h * D;
   int kend = p.Lk;
   if (p.causal) kend = min(p.Lk, q0 + TQ);
-  const bf16* kbase = p.k + b * p.k_bs + h * D;
-  const bf16* vbase = p.v + b * p.v_bs + h * D;
+  const bf16* kbase = p.k + (b / p.kv_div) * p.k_bs + h * D;
+  const bf16* vbase = p.v + (b / p.kv_div) * p.v_bs + h * D;
   // prologue: chunk 0 in flight while Q is staged
   load_tile_async<D>(sKV, kbase, p.k_rs, min(TK, p.Lk));
   load_tile_async<D>(sKV + TILE, vbase, p.v_rs, min(TK, p.Lk));
@@ -794,6 +795,8 @@ int fill(AttnParams& p, const PrismerAttnArgs* a) {
   p.dk = (bf16*)a->dk; p.dk_bs = a->dk_bs; p.dk_rs = a->dk_rs;
   p.dv = (bf16*)a->dv; p.dv_bs = a->dv_bs; p.dv_rs = a->dv_rs;
   p.delta = a->delta;
+  p.kv_div = a->kv_div > 1 ? a->kv_div : 1;
+  if (p.kv_div > 1 && (p.kmask || a->B % p.kv_div)) return PRISMER_ERR_SHAPE;     // key masks are per query batch row
   return PRISMER_OK;
 }
 
@@ -821,7 +824,7 @@ extern "C" int prismer_attention_bwd(const PrismerAttnArgs* a, cudaStream_t stre
   AttnParams p;
   int rc = fill(p, a);
   if (rc) return rc;
-  if (!p.dout || !p.dq || !p.dk || !p.dv || !p.delta || !p.lse) return PRISMER_ERR_SHAPE;
+  if (!p.dout || !p.dq || !p.dk || !p.dv || !p.delta || !p.lse || p.kv_div > 1) return PRISMER_ERR_SHAPE;
   const long long strides[] = {a->do_bs, a->do_rs, a->dq_bs, a->dq_rs, a->dk_bs, a->dk_rs, a->dv_bs, a->dv_rs};
   for (long long s : strides) if (s % 8) return PRISMER_ERR_ALIGN;
   if (attn_sm100_try_bwd(a, stream, &rc)) return rc;

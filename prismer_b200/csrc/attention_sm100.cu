@@ -580,7 +580,7 @@ int bwd_smem(int Sq, int Sk) { return 2 * (up16(Sq) + up16(Sk)) * 128 + 4 * kAto
 int g_force_legacy = 0;
 
 bool supported(const PrismerAttnArgs* a) {
-  return !g_force_legacy && a->d == 64 && !a->causal && !a->key_mask && a->drop_p == 0.f && a->Lq >= 64 && a->Lq <= kMaxL &&
+  return !g_force_legacy && a->kv_div <= 1 && a->d == 64 && !a->causal && !a->key_mask && a->drop_p == 0.f && a->Lq >= 64 && a->Lq <= kMaxL &&
          a->Lk >= 16 && a->Lk <= kMaxL;
 }
 

@@ -710,9 +710,11 @@ def cross_kv(dec, enc):
 
 
 def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: bool, need_logits: bool = True,
-                    kv: Optional[SimpleNamespace] = None, last_only: bool = False):
+                    kv: Optional[SimpleNamespace] = None, last_only: bool = False, enc_repeat: int = 1):
     """RobertaForCausalLMModified.forward (roberta.py:358-399) on a batch of pre-tokenised ids.
-    ``kv``: precomputed ``cross_kv``; ``last_only``: LM head on the last position of every row only (greedy decoding)."""
+    ``kv``: precomputed ``cross_kv``; ``last_only``: LM head on the last position of every row only (greedy decoding);
+    ``enc_repeat`` = k (inference only): ``input_ids`` holds k consecutive rows per image and ``enc`` ONE row per image -- the visual
+    K/V are projected once per image and shared by its k candidates (rank inference without ``tile``, prismer_caption.py:94-96)."""
     cfg = dec.config
     st = _store(dec)
     training = dec.training
@@ -739,17 +741,17 @@ def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: 
     if kv is None:
         kv = cross_kv(dec, enc)
     enc_flat, Be, S, ebs, ers_, kv_all = kv.enc_flat, kv.B, kv.S, kv.bs, kv.rs, kv.kv_all   # kv_all: [S*B, L*2H]
-    assert Be == B, "encoder_hidden_states batch mismatch"
+    assert Be * enc_repeat == B and (enc_repeat == 1 or not save), "encoder_hidden_states batch mismatch"
     sv.enc_flat, sv.kv_all, sv.S, sv.enc_bs, sv.enc_rs = enc_flat, kv_all, S, ebs, ers_
     for li, (layer, cross, adp) in enumerate(encoder.layer):
         h, lsv = _dec_self_fwd(layer, h, B, T, nh, attention_mask, p_h, p_a, seed, li, save)
         # cross attention over the visual tokens (roberta.py:225; no mask)
         q = gemm(h, cross.self.query.weight._c16, bias=cross.self.query.bias.data)
-        k3 = _x3(kv_all, B, S, ebs, ers_, li * 2 * Hd, li * 2 * Hd + Hd)
-        v3 = _x3(kv_all, B, S, ebs, ers_, li * 2 * Hd + Hd, (li + 1) * 2 * Hd)
+        k3 = _x3(kv_all, Be, S, ebs, ers_, li * 2 * Hd, li * 2 * Hd + Hd)
+        v3 = _x3(kv_all, Be, S, ebs, ers_, li * 2 * Hd + Hd, (li + 1) * 2 * Hd)
         o = torch.empty((B * T, Hd), dtype=BF16, device=dev)
         _, lse = ops.attention_fwd(q.view(B, T, Hd), k3, v3, nh, drop_p=p_a, seed=seed, rng_stream=_site(_RS_CROSS_P, li),
-                                   need_lse=save, out=o.view(B, T, Hd))
+                                   need_lse=save, out=o.view(B, T, Hd), kv_div=enc_repeat)
         pre = gemm(o, cross.output.dense.weight._c16, bias=cross.output.dense.bias.data, residual=h, drop_p=p_h, seed=seed,
                    rng_stream=_site(_RS_CROSS_O, li))
         h_c, muc, rsc = _ln(pre, cross.output.LayerNorm, save)
@@ -924,10 +926,10 @@ def encoder_apply(vit, experts: Dict) -> torch.Tensor:
     return out.view(S, B, -1)
 
 
-def decoder_apply(dec, input_ids, attention_mask, enc, labels=None, weights=None):
+def decoder_apply(dec, input_ids, attention_mask, enc, labels=None, weights=None, enc_repeat: int = 1):
     from .modules.roberta import CausalLMOutput
     _store(dec).refresh()
-    logits, loss_samples, _, _ = decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save=False)
+    logits, loss_samples, _, _ = decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save=False, enc_repeat=enc_repeat)
     B, T = input_ids.shape
     return CausalLMOutput(loss=loss_samples, logits=logits.unflatten(0, (B, T)))
 

@@ -163,9 +163,11 @@ class RobertaForCausalLMModified(nn.Module):
         return self.lm_head.decoder
 
     def forward(self, input_ids=None, attention_mask=None, encoder_hidden_states=None, labels=None, weights=None,
-                return_dict=True, **_):
+                return_dict=True, encoder_repeat: int = 1, **_):
+        """``encoder_repeat`` = k (extension, inference only): ``input_ids`` carries k consecutive rows per row of
+        ``encoder_hidden_states`` -- what the reference obtains by ``tile``-ing the encoder states k times (prismer_caption.py:94-96)."""
         from .. import engine
-        return engine.decoder_apply(self, input_ids, attention_mask, encoder_hidden_states, labels, weights)
+        return engine.decoder_apply(self, input_ids, attention_mask, encoder_hidden_states, labels, weights, enc_repeat=encoder_repeat)
 
     def prepare_inputs_for_generation(self, input_ids, attention_mask=None, encoder_hidden_states=None, **kw):
         if attention_mask is None:

@@ -146,8 +146,9 @@ def set_attention_path(legacy: bool):
 
 
 def attention_fwd(q, k, v, heads: int, *, causal=False, key_mask=None, drop_p=0.0, seed=None, rng_stream=0,
-                  need_lse=True, scale=None, out=None):
-    """q: [B,Lq,H*d]; k, v: [B,Lk,H*d] (views into packed projections are fine).  Returns (o [B,Lq,H*d], lse [B,H,Lq])."""
+                  need_lse=True, scale=None, out=None, kv_div=1):
+    """q: [B,Lq,H*d]; k, v: [B / kv_div, Lk, H*d] (views into packed projections are fine; with ``kv_div`` > 1 every group of kv_div
+    consecutive query batch rows reads the same keys / values).  Returns (o [B,Lq,H*d], lse [B,H,Lq])."""
     _req_cuda(q, k, v)
     B, Lq, HD = q.shape
     Lk = k.shape[1]
@@ -169,6 +170,8 @@ def attention_fwd(q, k, v, heads: int, *, causal=False, key_mask=None, drop_p=0.
     if drop_p > 0:
         a.seed = seed.data_ptr()
     a.rng_stream = rng_stream
+    a.kv_div = kv_div
+    assert k.shape[0] * kv_div == B, "keys / values batch must be the query batch divided by kv_div"
     check(_C.lib().prismer_attention_fwd(ctypes.byref(a), _stream()), "attention_fwd")
     return o, lse
 

@@ -66,10 +66,11 @@ def rank(model, experts, start_ids, start_mask, answer_ids, answer_mask, k_test)
     a_att = torch.cat([answer_mask.index_select(0, t) for t in topk_ids], dim=0)
     input_ids = torch.cat([tile(start_ids, 0, k_test), a_ids], dim=1).long()
     attention_masks = torch.cat([tile(start_mask, 0, k_test), a_att], dim=1)
-    enc_t = tile(enc.contiguous(), 0, k_test)
     targets = input_ids.masked_fill(input_ids == pad, -100)
     targets[:, :-answer_ids.shape[1]] = -100
-    out = model.text_decoder(input_ids, attention_mask=attention_masks, encoder_hidden_states=enc_t, labels=targets)
+    # the reference tiles the encoder states k_test times (prismer_caption.py:94-96); here the k candidates of an image share its visual
+    # K/V (projected once per image) through the attention kernel's kv_div: same arithmetic, 1/k of the K/V projection work and memory
+    out = model.text_decoder(input_ids, attention_mask=attention_masks, encoder_hidden_states=enc, labels=targets, encoder_repeat=k_test)
     log_probs_sum = (-out.loss / torch.sum(targets != -100, dim=-1)).view(-1, k_test)
     max_topk_ids = log_probs_sum.argmax(dim=1)
     return topk_ids[max_topk_ids >= 0, max_topk_ids]

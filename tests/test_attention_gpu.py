@@ -139,3 +139,33 @@ def test_tensor_memory_kernels_match_mma_sync_kernels_on_the_engine_layout(B, H,
     assert _rel(o2.float(), o1.float()) < 4e-3 and _rel(l2, l1) < 1e-5
     for c in range(3):
         assert _rel(g2[:, c * D:(c + 1) * D].float(), g1[:, c * D:(c + 1) * D].float()) < 8e-3, c
+
+
+def test_shared_keys_values_equal_tiled_keys_values():
+    """``kv_div`` (rank inference, prismer_caption.py:94-96 / prismer_vqa.py:95-97): k consecutive query rows read ONE set of keys / values
+    -- bit-identical to attention over ``tile``-d keys / values; and the decoder with ``encoder_repeat=k`` equals the decoder on tiled
+    encoder states (logits and per-sample losses)."""
+    from prismer_b200 import modeling, ops
+    from tests.helpers import TINY_DEC, beam_decoder_state
+    B, k, H, Lq, Lk, d = 3, 5, 4, 9, 70, 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = torch.randn(B * k, Lq, H * d, device="cuda", generator=g).to(torch.bfloat16)
+    kv = torch.randn(B, Lk, 2 * H * d, device="cuda", generator=g).to(torch.bfloat16)
+    o1, l1 = ops.attention_fwd(q, kv[..., :H * d], kv[..., H * d:], H, kv_div=k)
+    kvt = kv.repeat_interleave(k, dim=0)
+    o2, l2 = ops.attention_fwd(q, kvt[..., :H * d], kvt[..., H * d:], H)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)
+    dec = modeling.build_decoder(TINY_DEC)
+    dec.load_state_dict(beam_decoder_state(dec.state_dict(), 0.0))
+    dec.cuda().eval()
+    T, S = 7, 20
+    ids = torch.randint(3, TINY_DEC["vocab_size"], (B * k, T), device="cuda", generator=g)
+    mask = torch.ones_like(ids)
+    labels = ids.clone(); labels[:, :3] = -100
+    enc = torch.randn(B, S, TINY_DEC["vision_hidden_size"], device="cuda", generator=g).to(torch.bfloat16)
+    with torch.no_grad():
+        a = dec(ids, attention_mask=mask, encoder_hidden_states=enc, labels=labels, encoder_repeat=k)
+        b = dec(ids, attention_mask=mask, encoder_hidden_states=enc.repeat_interleave(k, dim=0), labels=labels)
+    torch.cuda.synchronize()
+    assert torch.equal(a.logits, b.logits) and torch.equal(a.loss, b.loss)

@@ -39,7 +39,8 @@ def stand_in(monkeypatch):
     def encoder_apply(vit, experts):
         return O.encoder_forward(experts, enc_sd(vit), S["cfg"]["patch"])
 
-    def decoder_apply(dec, input_ids, attention_mask, enc, labels=None, weights=None):
+    def decoder_apply(dec, input_ids, attention_mask, enc, labels=None, weights=None, enc_repeat=1):
+        enc = enc.repeat_interleave(enc_repeat, dim=0)          # the reference's tile() (prismer_caption.py:94-96)
         if attention_mask is None:
             attention_mask = torch.ones_like(input_ids)
         logits, loss = O.decoder_forward(input_ids, attention_mask, enc.float(), dec_sd(dec), HEADS, labels)
