@@ -194,20 +194,15 @@ int prismer_argmax(const float* logits, long long ld, int rows, int V, int suppr
 /* ---------------------------------------------------------------------------------------------------------
  * KV-cached decode step: one new token per sequence instead of the reference's cache-less re-forward of the whole
  * prefix (roberta.py:401-406, called from prismer_caption.py:45-50 / prismer_vqa.py:51-57).  M = batch rows; weight-streaming kernels.
- *   prismer_skinny_linear   : out[M,N] = act(LNx(x)[M,K] . w[N,K]^T + bias) (+ LNr(residual));  out bf16 or fp32.  The post-LayerNorms of
- *                             the decoder (roberta.py:139,182; utils.py:61-62) are applied ON LOAD by their consumers instead of as
- *                             launches of their own: x_gamma / x_beta / x_eps != NULL normalise the x rows (K = row length <= 1024) and
- *                             publish (mean, rstd) per row in stats_out [M,2]; r_gamma / r_beta / r_stats apply the same LayerNorm to
- *                             the residual rows with the statistics an earlier launch published.  NULL = plain x / residual.
+ *   prismer_skinny_linear   : out[M,N] = act(x[M,K] . w[N,K]^T + bias) (+ residual);  out bf16 or fp32 (the post-LayerNorm of
+ *                             roberta.py:139,182,424 is a prismer_layernorm_fwd launch on the M rows).
  *   prismer_decode_attention: o[b,h,:] = softmax_j(scale * q[b,h,:].k[b,j,h,:] (+ mask)) v[b,j,h,:], one query per (b, h), head dim 64,
  *                             keys j < len at k + b*kv_bs + j*kv_rs + h*64; optional new token (k_new, v_new) as key `len`, which
  *                             is also appended to (k_cache, v_cache) row `len` (RobertaSelfAttention with past key/values,
  *                             roberta.py:95-126); key_mask int64 [B, mask_ld] (1 = attend) or NULL.
  * --------------------------------------------------------------------------------------------------------- */
 int prismer_skinny_linear(const void* x, long long ldx, const void* w, long long ldw, const float* bias, const void* residual,
-                          long long ldr, void* out, long long ldo, int out_fp32, int M, int N, int K, int act, const float* x_gamma,
-                          const float* x_beta, float x_eps, float* stats_out, const float* r_gamma, const float* r_beta,
-                          const float* r_stats, cudaStream_t stream);
+                          long long ldr, void* out, long long ldo, int out_fp32, int M, int N, int K, int act, cudaStream_t stream);
 int prismer_decode_attention(const void* q, long long q_bs, const void* k, const void* v, long long kv_bs, long long kv_rs, int len,
                              const void* k_new, const void* v_new, long long new_bs, void* k_cache, void* v_cache, long long c_bs,
                              long long c_rs, const void* key_mask, int mask_ld, void* o, long long o_bs, int B, int H, int d,

@@ -37,7 +37,7 @@ SIGNATURES = {
     "prismer_cast_pad": [P, P, L, I, I, P],
     "prismer_unpad_add": [P, P, L, I, I, P],
     "prismer_set_attention_path": [I],
-    "prismer_skinny_linear": [P, L, P, L, P, P, L, P, L, I, I, I, I, I, P, P, F, P, P, P, P, P],
+    "prismer_skinny_linear": [P, L, P, L, P, P, L, P, L, I, I, I, I, I, P],
     "prismer_decode_attention": [P, L, P, P, L, L, I, P, P, L, P, P, L, L, P, I, P, L, I, I, I, F, P],
 }
 

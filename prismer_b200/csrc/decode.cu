@@ -48,11 +48,6 @@ struct SkinnyParams {
   void* out; long long ldo; int out_fp32;
   int M, N, K, act;
   int kc_len;                    // K chunk staged in shared memory per round trip (multiple of 16, <= kKc)
-  // LayerNorm on load (post-LN decoder, roberta.py:139,182; utils.py:61-62): x := LN(x rows) with (x_gamma, x_beta, x_eps) -- every CTA
-  // normalises the 32 staged rows itself (K = row length, one chunk); CTAs of column block 0 publish (mean, rstd) per row in stats_out.
-  const float* x_gamma; const float* x_beta; float x_eps; float* stats_out;
-  // residual := LN(residual rows) with the statistics an earlier launch published (the same LayerNorm output, consumed as the skip path)
-  const float* r_gamma; const float* r_beta; const float* r_stats;
 };
 
 // Every global byte this CTA needs (its 16 x Kc weight slice and the 32 x Kc activation rows) is requested up front with cp.async --
@@ -99,44 +94,6 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
     }
     cp_async_wait_all();
     __syncthreads();
-    if (p.x_gamma) {            // LayerNorm of the staged rows in place (fp32 statistics: mean, then centred second moment -- as ln_fwd_kernel)
-      const int nvec = kn >> 3;
-      for (int r = warp; r < kRows; r += 4) {
-        bf16* row = sx + r * ld;
-        float sum = 0.f;
-        for (int v = lane; v < nvec; v += 32) {
-          float f[8];
-          unpack8(*reinterpret_cast<const uint4*>(row + v * 8), f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sum += f[e];
-        }
-        const float mean = warp_sum(sum) / kn;
-        float var = 0.f;
-        for (int v = lane; v < nvec; v += 32) {
-          float f[8];
-          unpack8(*reinterpret_cast<const uint4*>(row + v * 8), f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { const float d = f[e] - mean; var += d * d; }
-        }
-        const float rstd = rsqrtf(warp_sum(var) / kn + p.x_eps);
-        if (p.stats_out && blockIdx.x == 0 && lane == 0 && r < mrows) {
-          p.stats_out[2 * (m0 + r)] = mean;
-          p.stats_out[2 * (m0 + r) + 1] = rstd;
-        }
-        for (int v = lane; v < nvec; v += 32) {
-          float f[8];
-          unpack8(*reinterpret_cast<const uint4*>(row + v * 8), f);
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.x_gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.x_gamma + v * 8 + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.x_beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(p.x_beta + v * 8 + 4));
-          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = (f[e] - mean) * rstd * g[e] + bb[e];
-          *reinterpret_cast<uint4*>(row + v * 8) = pack8(f);
-        }
-      }
-      __syncthreads();
-    }
     const int steps = kn >> 4;
     for (int s = warp; s < steps; s += 4) {
       uint32_t a0[4], a1[4], bw[4];
@@ -170,12 +127,7 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
     float v = red[o] + red[kRows * kCols + o] + red[2 * kRows * kCols + o] + red[3 * kRows * kCols + o];
     if (p.bias) v += p.bias[n];
     v = act_fwd(p.act, v);
-    if (p.residual) {
-      float rv = __bfloat162float(p.residual[static_cast<long long>(m) * p.ldr + n]);
-      if (p.r_gamma)            // the skip path carries LN(residual), rounded to bf16 like the materialised LayerNorm output would be
-        rv = __bfloat162float(__float2bfloat16((rv - p.r_stats[2 * m]) * p.r_stats[2 * m + 1] * p.r_gamma[n] + p.r_beta[n]));
-      v += rv;
-    }
+    if (p.residual) v += __bfloat162float(p.residual[static_cast<long long>(m) * p.ldr + n]);
     if (p.out_fp32) reinterpret_cast<float*>(p.out)[static_cast<long long>(m) * p.ldo + n] = v;
     else reinterpret_cast<bf16*>(p.out)[static_cast<long long>(m) * p.ldo + n] = __float2bfloat16(v);
   }
@@ -292,23 +244,18 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(DecAttnParams p) {
 }  // namespace
 
 extern "C" int prismer_skinny_linear(const void* x, long long ldx, const void* w, long long ldw, const float* bias, const void* residual,
-                                     long long ldr, void* out, long long ldo, int out_fp32, int M, int N, int K, int act,
-                                     const float* x_gamma, const float* x_beta, float x_eps, float* stats_out, const float* r_gamma,
-                                     const float* r_beta, const float* r_stats, cudaStream_t stream) {
+                                     long long ldr, void* out, long long ldo, int out_fp32, int M, int N, int K, int act, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (K % 16) || (ldx % 8) || (ldw % 8)) return PRISMER_ERR_SHAPE;
-  if ((x_gamma != nullptr) != (x_beta != nullptr) || (x_gamma && K > kKc)) return PRISMER_ERR_SHAPE;     // LN on load: the row is one chunk
-  if (r_gamma && (!r_beta || !r_stats || !residual)) return PRISMER_ERR_SHAPE;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return PRISMER_ERR_ALIGN;     // 16-byte cp.async rows
   SkinnyParams p;
   p.x = reinterpret_cast<const bf16*>(x); p.ldx = ldx; p.w = reinterpret_cast<const bf16*>(w); p.ldw = ldw; p.bias = bias;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
   p.M = M; p.N = N; p.K = K; p.act = act;
-  p.x_gamma = x_gamma; p.x_beta = x_beta; p.x_eps = x_eps; p.stats_out = stats_out; p.r_gamma = r_gamma; p.r_beta = r_beta; p.r_stats = r_stats;
   // K chunk per shared-memory round trip: the whole K (<= 1024) when the grid fits one wave -- a single memory round trip per CTA --,
   // 256 when there are many more CTAs than SMs (LM head: 3142 CTAs): 25 KB of shared memory per CTA, 8 CTAs per SM hide each other's latency
   const long long ctas = static_cast<long long>((N + kCols - 1) / kCols) * ((M + kRows - 1) / kRows);
   int kc = K < kKc ? K : kKc;
-  if (ctas > 3 * 148 && kc > 256 && !x_gamma) kc = 256;
+  if (ctas > 3 * 148 && kc > 256) kc = 256;
   p.kc_len = kc;
   size_t smem = static_cast<size_t>(kRows + kCols) * (kc + kPad) * 2;
   const size_t red = static_cast<size_t>(4) * kRows * kCols * 4;

@@ -3,8 +3,8 @@ re-forward of the whole prefix (roberta.py:401-406, driven by prismer_caption.py
 
 Same arithmetic as ``engine.decoder_forward`` (eval mode) restricted to the last position: the self-attention keys / values of
 earlier positions come from a per-layer cache, the cross-attention K / V of the visual tokens are projected once per call
-(``engine.cross_kv``).  Every product runs on the decode-time kernels of ``csrc/decode.cu`` (``prismer_skinny_linear`` with the post-LayerNorms
-applied on load by their consumers, ``prismer_decode_attention``): ~140 small launches per step instead of ~210
+(``engine.cross_kv``).  Every product runs on the decode-time kernels of ``csrc/decode.cu`` (``prismer_skinny_linear``, ``prismer_decode_attention``, the
+post-LayerNorms as 32-row ``prismer_layernorm_fwd`` launches): ~190 small launches per step instead of ~210
 persistent-GEMM launches over a growing prefix.  Token ids are checked bit-exact against the reference goldens and against the
 cache-less path (tests/test_kv_decode_gpu.py).
 """
@@ -18,43 +18,19 @@ from . import _C, engine, ops
 from .ops import BF16, F32, _p, check
 
 
-class LazyLN:
-    """LayerNorm(pre) that is never materialised: its consumers apply it on load (``prismer_skinny_linear``).  The consumer that takes it
-    as ``x`` normalises the staged rows itself and publishes the per-row (mean, rstd) in ``stats``; the later consumer that takes it as
-    the residual re-uses those statistics."""
-
-    def __init__(self, pre, ln):
-        self.pre, self.ln = pre, ln
-        self.stats = torch.empty((pre.shape[0], 2), dtype=F32, device=pre.device)
-
-
 def skinny_linear(x, w16, bias=None, *, act=0, residual=None, ln=None, out_dtype=BF16):
-    """y = act(x . w16^T + bias) (+ residual) for a handful of rows.  ``x`` / ``residual`` may be ``LazyLN`` handles (LayerNorm applied on
-    load).  ``ln`` (a LayerNorm module): returns (y, LazyLN(y, ln)) -- the post-LayerNorm is left to the consumers."""
-    xl = x if isinstance(x, LazyLN) else None
-    rl = residual if isinstance(residual, LazyLN) else None
-    xt = xl.pre if xl is not None else x
-    rt = rl.pre if rl is not None else residual
-    M, K = xt.shape
+    """y = act(x . w16^T + bias) (+ residual) for a handful of rows; with ``ln`` (a LayerNorm module) returns (y, LN(y))."""
+    M, K = x.shape
     N = w16.shape[0]
-    assert xt.dtype == BF16 and w16.dtype == BF16 and xt.stride(1) == 1 and w16.stride(1) == 1 and w16.shape[1] == K
-    out = torch.empty((M, N), dtype=out_dtype, device=xt.device)
+    assert x.dtype == BF16 and w16.dtype == BF16 and x.stride(1) == 1 and w16.stride(1) == 1 and w16.shape[1] == K
+    out = torch.empty((M, N), dtype=out_dtype, device=x.device)
     check(_C.lib().prismer_skinny_linear(
-        xt.data_ptr(), xt.stride(0), w16.data_ptr(), w16.stride(0), _p(bias), _p(rt), rt.stride(0) if rt is not None else 0,
-        out.data_ptr(), out.stride(0), int(out_dtype == F32), M, N, K, ops.ACT.get(act, act),
-        _p(xl.ln.weight.data) if xl is not None else None, _p(xl.ln.bias.data) if xl is not None else None,
-        float(xl.ln.eps) if xl is not None else 0.0, _p(xl.stats) if xl is not None else None,
-        _p(rl.ln.weight.data) if rl is not None else None, _p(rl.ln.bias.data) if rl is not None else None,
-        _p(rl.stats) if rl is not None else None, ops._stream()), "skinny_linear")
-    return out if ln is None else (out, LazyLN(out, ln))
-
-
-def materialize(h):
-    """The bf16 tensor a ``LazyLN`` stands for (a ``prismer_layernorm_fwd`` launch)."""
-    if not isinstance(h, LazyLN):
-        return h
-    y, _, _ = ops.layernorm_fwd(h.pre, h.ln.weight.data, h.ln.bias.data, h.ln.eps, save_stats=False)
-    return y
+        x.data_ptr(), x.stride(0), w16.data_ptr(), w16.stride(0), _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
+        out.data_ptr(), out.stride(0), int(out_dtype == F32), M, N, K, ops.ACT.get(act, act), ops._stream()), "skinny_linear")
+    if ln is None:
+        return out
+    y, _, _ = ops.layernorm_fwd(out, ln.weight.data, ln.bias.data, ln.eps, save_stats=False)
+    return out, y
 
 
 def decode_attention(q, k, v, kv_bs, kv_rs, length, heads, *, k_new=None, v_new=None, k_cache=None, v_cache=None, key_mask=None, scale=None):
@@ -123,7 +99,8 @@ class KVDecoder:
         emb = dec.roberta.embeddings
         e, _ = ops.embed_fwd(ids_so_far, emb.word_embeddings.weight._c16, emb.position_embeddings.weight._c16,
                              emb.token_type_embeddings.weight._c16, cfg.pad_token_id)            # positions need the whole row (cumsum of non-pad)
-        h = LazyLN(e.view(self.B, t + 1, Hd)[:, t], emb.LayerNorm)                               # [B, Hd] strided rows; LN on load (roberta.py:74)
+        last = e.view(self.B, t + 1, Hd)[:, t]                                                   # [B, Hd] strided rows
+        h, _, _ = ops.layernorm_fwd(last, emb.LayerNorm.weight.data, emb.LayerNorm.bias.data, emb.LayerNorm.eps, save_stats=False)
         encoder = dec.roberta.encoder
         kv = self.kv
         ld = kv.kv_all.stride(0)
@@ -142,9 +119,7 @@ class KVDecoder:
         if not need_logits:
             return None
         lm = dec.lm_head
-        g = skinny_linear(h, lm.dense.weight._c16, lm.dense.bias.data, act="gelu")
-        xl, _, _ = ops.layernorm_fwd(g, lm.layer_norm.weight.data, lm.layer_norm.bias.data, lm.layer_norm.eps, save_stats=False)
-        # (the vocabulary projection runs 3142 CTAs with 256-wide K chunks, so its LayerNorm is a launch of its own, not applied on load)
+        _, xl = skinny_linear(h, lm.dense.weight._c16, lm.dense.bias.data, act="gelu", ln=lm.layer_norm)
         return skinny_linear(xl, emb.word_embeddings.weight._c16, lm.bias.data, out_dtype=F32)      # tied LM head, fp32 logits [B, V]
 
 

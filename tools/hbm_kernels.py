@@ -38,7 +38,6 @@ w_fc, w_head = bf(3072, Hd) * 0.03, word
 b_fc = rn(3072)
 kv_all = bf(S * B, 2 * Hd)                       # one layer's projected visual K | V, seq-first rows (s*B + b) like engine.cross_kv
 lnm = torch.nn.LayerNorm(Hd).to(dev)
-lazy = kv_decode.LazyLN(xq, lnm)
 CALLS = [
     ("ln_fwd  [8320,768]", 2 * rows * D * 2, lambda: ops.layernorm_fwd(x, gamma, beta)),
     ("ln_bwd  [8320,768] frozen (dx only, + residual grad)", 4 * rows * D * 2, lambda: ops.layernorm_bwd(dy, x, mean, rstd, gamma, dres=dres)),
@@ -53,8 +52,8 @@ CALLS = [
     ("im2col_nhwc 56x56x96 k3 s2", B * 56 * 56 * 96 * 2 + B * 28 * 28 * 9 * 96 * 2, lambda: ops.im2col_nhwc(act56, B, 56, 56, 96, 3, 2)),
     ("ce_loss_fwd [960,50265] fp32", B * T * V * 4, lambda: ops.ce_loss_fwd(logits, labels, V)),
     ("skinny_linear [32,768]x[3072,768] gelu (decode MLP fc: weights streamed once)", 3072 * Hd * 2, lambda: kv_decode.skinny_linear(xq, w_fc, b_fc, act="gelu")),
-    ("skinny_linear [32,768]x[768,768], LayerNorm of x on load + LayerNorm'd residual", Hd * Hd * 2,
-     lambda: kv_decode.skinny_linear(lazy, w_fc[:Hd], b_fc[:Hd], residual=lazy)),
+    ("skinny_linear [32,768]x[768,768] + residual, then ln_fwd on the 32 rows", Hd * Hd * 2,
+     lambda: kv_decode.skinny_linear(xq, w_fc[:Hd], b_fc[:Hd], residual=xq, ln=lnm)),
     ("skinny_linear [32,768]x[50265,768] fp32 logits (tied LM head)", V * Hd * 2, lambda: kv_decode.skinny_linear(xq, w_head, None, out_dtype=torch.float32)),
     ("decode_attention cross: 32x12 queries over 260 visual keys (K, V read once)", 2 * B * S * Hd * 2,
      lambda: kv_decode.decode_attention(xq, kv_all, kv_all[:, Hd:], 2 * Hd, B * 2 * Hd, S, 12)),
