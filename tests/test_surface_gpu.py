@@ -49,6 +49,15 @@ def test_caption_string_api_train_generate_with_stock_adamw():
     m.eval()
     out = m(ex, train=False, prefix="A picture of")
     assert isinstance(out, list) and len(out) == 2 and all(isinstance(s, str) for s in out)
+    # the bf16 compute copies follow the fp32 masters after a stock optimizer step (refreshed on the next forward) ...
+    stale = [n for n, p in m.named_parameters() if getattr(p, "_c16", None) is not None and not torch.equal(p._c16, p.data.to(torch.bfloat16))]
+    assert not stale, stale[:5]
+    # ... and after load_state_dict on the prepared model (frozen parameters included)
+    sd = {k: (v + 0.01 if v.is_floating_point() else v) for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    m(ex, train=False, prefix="A picture of")
+    stale = [n for n, p in m.named_parameters() if getattr(p, "_c16", None) is not None and not torch.equal(p._c16, p.data.to(torch.bfloat16))]
+    assert not stale, stale[:5]
 
 
 def test_graphed_step_equals_eager_step():
