@@ -73,7 +73,10 @@ __device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
   return sh[0];
 }
 
-// one block per (b, t) row of logits; label = labels[b, t+1] (shift), rows t == T-1 are skipped
+// one block per (b, t) row of logits; label = labels[b, t+1] (shift), rows t == T-1 are skipped.
+// ONE pass over the row (the rows of a [960, 50265] fp32 buffer do not all fit in L2, a second pass re-reads most of them from HBM):
+// every thread keeps a running (max, sum of exp relative to that max, plain sum); VEC: 128-bit loads when the rows are 16-byte aligned.
+template <bool VEC>
 __global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restrict__ logits, long long ld,
                                                             const long long* __restrict__ labels, float* __restrict__ row_loss,
                                                             float* __restrict__ row_lse, int T, int V, float smoothing) {
@@ -81,15 +84,36 @@ __global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restr
   const int r = blockIdx.x, t = r % T;
   const float* x = logits + static_cast<long long>(r) * ld;
   const long long lab = (t < T - 1) ? labels[r + 1] : -100;
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, x[i]);
-  mx = block_reduce(mx, sh, true);
-  float se = 0.f, sx = 0.f;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) { const float v = x[i]; se += expf(v - mx); sx += v; }
-  se = block_reduce(se, sh, false);
+  float mx = -INFINITY, se = 0.f, sx = 0.f;
+  if (VEC) {
+    const int nv = V >> 2;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      const float m2 = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+      se = se * expf(mx - m2) + expf(v.x - m2) + expf(v.y - m2) + expf(v.z - m2) + expf(v.w - m2);
+      sx += (v.x + v.y) + (v.z + v.w);
+      mx = m2;
+    }
+    const int i = (nv << 2) + threadIdx.x;                       // <= 3 tail elements
+    if (i < V) {
+      const float v = x[i], m2 = fmaxf(mx, v);
+      se = se * expf(mx - m2) + expf(v - m2);
+      sx += v;
+      mx = m2;
+    }
+  } else {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+      const float v = x[i], m2 = fmaxf(mx, v);
+      se = se * expf(mx - m2) + expf(v - m2);
+      sx += v;
+      mx = m2;
+    }
+  }
+  const float bm = block_reduce(mx, sh, true);
+  se = block_reduce(mx == -INFINITY ? 0.f : se * expf(mx - bm), sh, false);
   sx = block_reduce(sx, sh, false);
   if (threadIdx.x == 0) {
-    const float lse = mx + logf(se);
+    const float lse = bm + logf(se);
     row_lse[r] = lse;
     float loss = 0.f;
     if (lab >= 0) loss = (1.0f - smoothing) * (lse - x[lab]) + smoothing * (lse - sx / V);
@@ -113,7 +137,9 @@ __global__ void ce_reduce_kernel(const float* __restrict__ row_loss, const float
 }
 
 // dlogits[b,t,:] = g_b * (softmax - (1-eps)*onehot - eps/V), g_b = gscale * weight_b / B ; zero for ignored rows; bf16 out,
-// padded columns [V, ldo) are zeroed so the buffer can feed the dgrad / wgrad GEMMs directly.
+// padded columns [V, ldo) are zeroed so the buffer can feed the dgrad / wgrad GEMMs directly.  VEC: 4 columns per thread and
+// iteration (128-bit loads, 64-bit stores) when ld and ldo are multiples of 4 and both buffers 16 / 8-byte aligned.
+template <bool VEC>
 __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restrict__ logits, long long ld,
                                                             const long long* __restrict__ labels, const float* __restrict__ row_lse,
                                                             const float* __restrict__ weights, const float* __restrict__ gscale,
@@ -123,21 +149,42 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restr
   const float* x = logits + static_cast<long long>(r) * ld;
   bf16* d = dlogits + static_cast<long long>(r) * ldo;
   const long long lab = (t < T - 1) ? labels[r + 1] : -100;
+  const int n = static_cast<int>(ldo);
   if (lab < 0) {
-    for (int i = threadIdx.x; i < ldo; i += blockDim.x) d[i] = __float2bfloat16(0.f);
+    if (VEC) {
+      for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) reinterpret_cast<uint2*>(d)[i] = make_uint2(0u, 0u);
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) d[i] = __float2bfloat16(0.f);
+    }
     return;
   }
   const float g = (gscale ? *gscale : 1.0f) * (weights ? weights[b] : 1.0f) / B;
   const float lse = row_lse[r];
   const float off = smoothing / V;
-  for (int i = threadIdx.x; i < ldo; i += blockDim.x) {
-    float v = 0.f;
-    if (i < V) {
-      v = expf(x[i] - lse) - off;
-      if (i == lab) v -= (1.0f - smoothing);
-      v *= g;
+  const int ilab = static_cast<int>(lab);
+  if (VEC) {
+    for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) {
+      const int c = i << 2;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c + 3 < V) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(x) + i);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (expf(v[k] - lse) - off - (c + k == ilab ? 1.0f - smoothing : 0.f)) * g;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (c + k < V) v[k] = (expf(x[c + k] - lse) - off - (c + k == ilab ? 1.0f - smoothing : 0.f)) * g;
+      }
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+      reinterpret_cast<uint2*>(d)[i] = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
     }
-    d[i] = __float2bfloat16(v);
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float v = 0.f;
+      if (i < V) v = (expf(x[i] - lse) - off - (i == ilab ? 1.0f - smoothing : 0.f)) * g;
+      d[i] = __float2bfloat16(v);
+    }
   }
 }
 
@@ -194,8 +241,13 @@ extern "C" int prismer_ce_loss_fwd(const float* logits, long long ld, const void
                                    float* row_lse, float* sample_loss, float* mean_loss, int B, int T, int V, float smoothing,
                                    cudaStream_t stream) {
   if (B <= 0 || T <= 0 || V <= 0) return PRISMER_ERR_SHAPE;
-  ce_fwd_kernel<<<B * T, CE_THREADS, 0, stream>>>(logits, ld, reinterpret_cast<const long long*>(labels), row_loss, row_lse, T, V,
-                                                smoothing);
+  const bool vec = ld % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0;
+  if (vec)
+    ce_fwd_kernel<true><<<B * T, CE_THREADS, 0, stream>>>(logits, ld, reinterpret_cast<const long long*>(labels), row_loss, row_lse, T, V,
+                                                        smoothing);
+  else
+    ce_fwd_kernel<false><<<B * T, CE_THREADS, 0, stream>>>(logits, ld, reinterpret_cast<const long long*>(labels), row_loss, row_lse, T, V,
+                                                         smoothing);
   ce_reduce_kernel<<<1, 256, 0, stream>>>(row_loss, weights, sample_loss, mean_loss, B, T);
   return LAUNCH_CHECK();
 }
@@ -204,8 +256,13 @@ extern "C" int prismer_ce_loss_bwd(const float* logits, long long ld, const void
                                    const float* weights, const float* gscale, void* dlogits, long long ldo, int B, int T, int V,
                                    float smoothing, cudaStream_t stream) {
   if (B <= 0 || T <= 0 || V <= 0 || ldo < V) return PRISMER_ERR_SHAPE;
-  ce_bwd_kernel<<<B * T, CE_THREADS, 0, stream>>>(logits, ld, reinterpret_cast<const long long*>(labels), row_lse, weights, gscale,
-                                                reinterpret_cast<bf16*>(dlogits), ldo, B, T, V, smoothing);
+  const bool vec = ld % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && (reinterpret_cast<uintptr_t>(dlogits) & 7) == 0;
+  if (vec)
+    ce_bwd_kernel<true><<<B * T, CE_THREADS, 0, stream>>>(logits, ld, reinterpret_cast<const long long*>(labels), row_lse, weights, gscale,
+                                                        reinterpret_cast<bf16*>(dlogits), ldo, B, T, V, smoothing);
+  else
+    ce_bwd_kernel<false><<<B * T, CE_THREADS, 0, stream>>>(logits, ld, reinterpret_cast<const long long*>(labels), row_lse, weights, gscale,
+                                                         reinterpret_cast<bf16*>(dlogits), ldo, B, T, V, smoothing);
   return LAUNCH_CHECK();
 }
 

@@ -15,6 +15,15 @@ inline int blocks_for(long long n, int threads) {
   return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// grid for the (lanes x channel-vector) stem kernels: enough blocks to cover ``units`` (pixels / slots) at ``per_thread`` units per
+// thread and iteration, capped at 4 resident-block waves of the 148 SMs (grid-stride loops take the rest)
+inline int stem_grid(long long units, int C, int per_thread) {
+  const int lanes = 384 / (C / 8);
+  long long b = (units + static_cast<long long>(lanes) * per_thread - 1) / (static_cast<long long>(lanes) * per_thread);
+  const long long cap = 148 * 4 * 2;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
 // ---------------------------------------------------------------------------------------------- rgb patchify (vit.py:86)
 // x fp32 NCHW [B,3,R,R] -> out bf16 [B*g*g, Kpad], K order (c, kh, kw) == nn.Conv2d weight.flatten(1); pad columns zero.
 __global__ void patchify_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int Cin, int R, int p, int g, int K,
@@ -112,30 +121,67 @@ __global__ void im2col_first_kernel(const void* __restrict__ in, int in_is_bf16,
   }
 }
 
+// Thread layout shared by the NHWC stem kernels below: a block of ST_THREADS threads is (lanes x cv) with cv = C / 8 channel vectors, so
+// every thread keeps ONE channel vector for its whole life (per-channel coefficients and partial sums live in registers) and a warp
+// touches runs of consecutive 16-byte vectors.  384 = lcm-friendly for every stem width (cv = 8, 12, 24, 48, 96 / 16, 32, 64, 128).
+// All index arithmetic is 32-bit unsigned (pixel / slot counts are < 2^31; byte offsets are widened at the last multiply): the
+// previous versions spent their time in 64-bit divisions and per-element scalar loads of the coefficients, not on HBM.
+constexpr int ST_THREADS = 384;
+
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 // NHWC bf16 input [B,H,W,C] (C % 8 == 0); optional per-channel affine + ReLU (= BatchNorm + ReLU of the producer layer);
 // out [B*Ho*Wo, k*k*C], K order (kh, kw, c).  Zero padding applies to the *post-ReLU* activation (conv pads its input).
-__global__ void im2col_nhwc_kernel(const bf16* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
-                                   bf16* __restrict__ out, int B, int H, int W, int C, int ksz, int stride, int Ho, int Wo) {
-  const int pad = ksz == 3 ? 1 : 0;
-  const int cv = C >> 3, taps = ksz * ksz;
-  const long long total = static_cast<long long>(B) * Ho * Wo * taps * cv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv);
-    const int tap = static_cast<int>((i / cv) % taps);
-    const long long row = i / (static_cast<long long>(cv) * taps);
-    const int xo = static_cast<int>(row % Wo), yo = static_cast<int>((row / Wo) % Ho), b = static_cast<int>(row / (static_cast<long long>(Wo) * Ho));
-    const int kh = tap / ksz, kw = tap % ksz;
-    const int yi = yo * stride - pad + kh, xi = xo * stride - pad + kw;
-    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
-      unpack8(*reinterpret_cast<const bf16x8*>(in + ((static_cast<long long>(b) * H + yi) * W + xi) * C + c * 8), v);
-      if (scale) {
+// A "slot" is one (output pixel, tap) pair = C contiguous output elements at out + slot * C; two slots per thread and iteration.
+template <int KSZ>
+__global__ void __launch_bounds__(ST_THREADS) im2col_nhwc_kernel(const bf16* __restrict__ in, const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift, bf16* __restrict__ out, int H, int W,
+                                                                 int C, int stride, int Ho, int Wo, unsigned nslots) {
+  constexpr unsigned TAPS = KSZ * KSZ;
+  constexpr int PAD = KSZ == 3 ? 1 : 0;
+  const unsigned cv = C >> 3;
+  const unsigned lanes = ST_THREADS / cv, cvi = threadIdx.x % cv, lane = threadIdx.x / cv;
+  if (lane >= lanes) return;
+  const bool affine = scale != nullptr;
+  float sc[8], sh[8];
+  if (affine) { load8f(scale + cvi * 8, sc); load8f(shift + cvi * 8, sh); }
+  const unsigned step = gridDim.x * lanes;
+  for (unsigned s0 = blockIdx.x * lanes + lane; s0 < nslots; s0 += 2 * step) {
+    bf16x8 raw[2];
+    bool inside[2];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t] * __ldg(scale + c * 8 + t) + __ldg(shift + c * 8 + t), 0.f);
+    for (int u = 0; u < 2; ++u) {
+      const unsigned slot = s0 + u * step;
+      inside[u] = false;
+      raw[u] = make_uint4(0, 0, 0, 0);
+      if (slot < nslots) {
+        const unsigned tap = slot % TAPS, row = slot / TAPS;
+        const unsigned xo = row % Wo, t = row / Wo, yo = t % Ho, b = t / Ho;
+        const int yi = static_cast<int>(yo) * stride - PAD + static_cast<int>(tap / KSZ);
+        const int xi = static_cast<int>(xo) * stride - PAD + static_cast<int>(tap % KSZ);
+        if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+          inside[u] = true;
+          raw[u] = *reinterpret_cast<const bf16x8*>(in + (static_cast<size_t>(b * H + yi) * W + xi) * C + cvi * 8);
+        }
       }
     }
-    *reinterpret_cast<bf16x8*>(out + row * (static_cast<long long>(taps) * C) + tap * C + c * 8) = pack8(v);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned slot = s0 + u * step;
+      if (slot < nslots) {
+        if (affine && inside[u]) {
+          float v[8];
+          unpack8(raw[u], v);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v[t] = fmaxf(fmaf(v[t], sc[t], sh[t]), 0.f);
+          raw[u] = pack8(v);
+        }
+        *reinterpret_cast<bf16x8*>(out + static_cast<size_t>(slot) * C + cvi * 8) = raw[u];
+      }
+    }
   }
 }
 
@@ -198,123 +244,148 @@ __global__ void bn_finalize_kernel(const float* __restrict__ acc, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------- BN + ReLU backward (1/2)
-// da[pix, c] = col2im(dAcol) for the consumer conv (ksz, stride; consumer output grid Ho x Wo); n = y*scale + shift;
+// da[pix, c] = col2im(dAcol) for the consumer conv (KSZ, STRIDE; consumer output grid Ho x Wo); n = y*scale + shift;
 // dn = (n > 0) ? da : 0; red[0][c] += dn; red[1][c] += dn * xhat  (xhat = (y - mean) * rstd).   Writes dn (bf16).
-__global__ void __launch_bounds__(256) bn_relu_bwd_gather_kernel(const bf16* __restrict__ dAcol, const bf16* __restrict__ y,
-                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                 bf16* __restrict__ dn, float* __restrict__ red, int B, int H, int W,
-                                                                 int C, int ksz, int stride, int Ho, int Wo) {
-  const int pad = ksz == 3 ? 1 : 0;
-  const int cv = C >> 3, taps = ksz * ksz;
-  const long long npix = static_cast<long long>(B) * H * W;
-  // each thread owns one channel vector and strides over pixels, so the per-channel partial sums stay in registers
-  const int cvi = threadIdx.x % cv;
-  const int lanes = blockDim.x / cv;
-  const int rl = threadIdx.x / cv;
+// Which (kh, kw) taps of which consumer outputs saw input pixel (yi, xi):  yo * STRIDE - 1 + kh == yi.
+//   STRIDE 2: yi even -> kh = 1, yo = yi / 2;  yi odd -> kh = 0, yo = (yi + 1) / 2 and kh = 2, yo = (yi - 1) / 2   (same in x): <= 4 taps
+//   STRIDE 1: kh = 0, 1, 2 -> yo = yi + 1 - kh: <= 9 taps.      KSZ 1: the pixel itself.
+// Every 16-byte piece of dAcol is read exactly once over the grid; all tap loads of a pixel are issued before the first is consumed.
+template <int KSZ, int STRIDE>
+__global__ void __launch_bounds__(ST_THREADS, (KSZ == 3 && STRIDE == 1) ? 1 : 2) bn_relu_bwd_gather_kernel(const bf16* __restrict__ dAcol, const bf16* __restrict__ y,
+                                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                        bf16* __restrict__ dn, float* __restrict__ red, int H, int W, int C,
+                                                                        int Ho, int Wo, unsigned npix) {
+  constexpr int NT = KSZ == 1 ? 1 : (STRIDE == 2 ? 4 : 9);
+  const unsigned cv = C >> 3;
+  const unsigned lanes = ST_THREADS / cv, cvi = threadIdx.x % cv, lane = threadIdx.x / cv;
+  const size_t ldr = static_cast<size_t>(KSZ * KSZ) * C;        // dAcol row length
   float s0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (rl < lanes) {
-    float sc[8], sh[8], mu[8], rs[8];
+  if (lane < lanes) {
+    float sc[8], sh[8], mu[8];
+    load8f(scale + cvi * 8, sc); load8f(shift + cvi * 8, sh); load8f(mean + cvi * 8, mu);
+    const unsigned step = gridDim.x * lanes;
+    for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += step) {
+      const unsigned xi = pix % W, t = pix / W, yi = t % H, b = t / H;
+      bf16x8 tv[NT];
+      const bf16x8 yraw = *reinterpret_cast<const bf16x8*>(y + static_cast<size_t>(pix) * C + cvi * 8);
+      if constexpr (KSZ == 1) {
+        tv[0] = *reinterpret_cast<const bf16x8*>(dAcol + static_cast<size_t>(pix) * C + cvi * 8);
+      } else if constexpr (STRIDE == 2) {
+        const int yodd = yi & 1, xodd = xi & 1;
+        const int kh[2] = {yodd ? 0 : 1, 2}, kw[2] = {xodd ? 0 : 1, 2};
+        const int yo[2] = {static_cast<int>(yi + 1 - kh[0]) >> 1, (static_cast<int>(yi) - 1) >> 1};
+        const int xo[2] = {static_cast<int>(xi + 1 - kw[0]) >> 1, (static_cast<int>(xi) - 1) >> 1};
+        const bool yok[2] = {yo[0] < Ho, yodd != 0}, xok[2] = {xo[0] < Wo, xodd != 0};
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { sc[t] = scale[cvi * 8 + t]; sh[t] = shift[cvi * 8 + t]; mu[t] = mean[cvi * 8 + t]; rs[t] = rstd[cvi * 8 + t]; }
-    for (long long pix = static_cast<long long>(blockIdx.x) * lanes + rl; pix < npix; pix += static_cast<long long>(gridDim.x) * lanes) {
-      const int xi = static_cast<int>(pix % W), yi = static_cast<int>((pix / W) % H), b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-      float da[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      // all (<= 9) tap loads are issued before any is consumed: 9 independent 128-bit loads in flight per thread
-      bf16x8 taps_v[9];
-      bool taps_ok[9];
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp) {
-        const int kh = tp / 3, kw = tp % 3;
-        bool ok = tp < taps && kh < ksz && kw < ksz;
-        const int ty = yi + pad - (ksz == 3 ? kh : 0), tx = xi + pad - (ksz == 3 ? kw : 0);
-        ok = ok && (ksz == 3 || tp == 0) && ty >= 0 && tx >= 0 && (ty % stride) == 0 && (tx % stride) == 0;
-        const int yo = ty / stride, xo = tx / stride;
-        ok = ok && yo < Ho && xo < Wo;
-        taps_ok[tp] = ok;
-        taps_v[tp] = make_uint4(0, 0, 0, 0);
-        if (ok) {
-          const int tapi = ksz == 3 ? tp : 0;
-          taps_v[tp] = *reinterpret_cast<const bf16x8*>(dAcol + ((static_cast<long long>(b) * Ho + yo) * Wo + xo) * (static_cast<long long>(taps) * C) +
-                                                        tapi * C + cvi * 8);
-        }
+          for (int c = 0; c < 2; ++c) {
+            tv[a * 2 + c] = make_uint4(0, 0, 0, 0);
+            if (yok[a] && xok[c])
+              tv[a * 2 + c] = *reinterpret_cast<const bf16x8*>(dAcol + (static_cast<size_t>(b * Ho + yo[a]) * Wo + xo[c]) * ldr +
+                                                               (kh[a] * 3 + kw[c]) * C + cvi * 8);
+          }
+      } else {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int yo = static_cast<int>(yi) + 1 - kh, xo = static_cast<int>(xi) + 1 - kw;
+            tv[kh * 3 + kw] = make_uint4(0, 0, 0, 0);
+            if (yo >= 0 && yo < Ho && xo >= 0 && xo < Wo)
+              tv[kh * 3 + kw] = *reinterpret_cast<const bf16x8*>(dAcol + (static_cast<size_t>(b * Ho + yo) * Wo + xo) * ldr + (kh * 3 + kw) * C +
+                                                                 cvi * 8);
+          }
       }
+      float da[8] = {0, 0, 0, 0, 0, 0, 0, 0}, yv[8];
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp) {
-        if (taps_ok[tp]) {
-          float f[8];
-          unpack8(taps_v[tp], f);
+      for (int tp = 0; tp < NT; ++tp) {
+        float f[8];
+        unpack8(tv[tp], f);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) da[t] += f[t];
-        }
+        for (int t8 = 0; t8 < 8; ++t8) da[t8] += f[t8];
       }
-      float yv[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(y + pix * C + cvi * 8), yv);
+      unpack8(yraw, yv);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float n = yv[t] * sc[t] + sh[t];
-        const float g = n > 0.f ? da[t] : 0.f;
-        da[t] = g;
-        s0[t] += g;
-        s1[t] += g * (yv[t] - mu[t]) * rs[t];
+      for (int t8 = 0; t8 < 8; ++t8) {
+        const float g = fmaf(yv[t8], sc[t8], sh[t8]) > 0.f ? da[t8] : 0.f;
+        da[t8] = g;
+        s0[t8] += g;
+        s1[t8] = fmaf(g, yv[t8] - mu[t8], s1[t8]);
       }
-      *reinterpret_cast<bf16x8*>(dn + pix * C + cvi * 8) = pack8(da);
+      *reinterpret_cast<bf16x8*>(dn + static_cast<size_t>(pix) * C + cvi * 8) = pack8(da);
     }
   }
-  __shared__ float sred[2][2048];
-  if (rl < lanes) {
+  __shared__ float sred[2][ST_THREADS * 8];                    // [sum | sum * (y - mean)][lane * C + channel]; lanes * C <= 3072
+  if (lane < lanes) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { sred[0][rl * C + cvi * 8 + t] = s0[t]; sred[1][rl * C + cvi * 8 + t] = s1[t]; }
+    for (int t8 = 0; t8 < 8; ++t8) { sred[0][lane * C + cvi * 8 + t8] = s0[t8]; sred[1][lane * C + cvi * 8 + t8] = s1[t8]; }
   }
   __syncthreads();
+  // one atomic per channel and block; the second sum becomes sum(dn * xhat) by the channel's rstd
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
     const int which = c / C, ch = c % C;
     float a = 0.f;
-    for (int l = 0; l < lanes; ++l) a += sred[which][l * C + ch];
+    for (unsigned l = 0; l < lanes; ++l) a += sred[which][l * C + ch];
+    if (which) a *= rstd[ch];
     atomicAdd(red + which * C + ch, a);
   }
 }
 
-// BN backward (2/2): dy = gamma*rstd * (dn - mean(dn) - xhat * mean(dn*xhat));  dgamma += sum dn*xhat;  dbeta += sum dn
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dn, const bf16* __restrict__ y, const float* __restrict__ red,
-                                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    bf16* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C) {
-  const int cv = C >> 3;
-  const long long total = M * cv;
-  const float invM = 1.0f / static_cast<float>(M);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv);
-    float g[8], yv[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(dn + i * 8), g);
-    unpack8(*reinterpret_cast<const bf16x8*>(y + i * 8), yv);
+// BN backward (2/2): dy = gamma*rstd * (dn - mean(dn) - xhat * mean(dn*xhat));  dgamma += sum dn*xhat;  dbeta += sum dn.
+// Per thread (one channel vector): dy = a * dn + k1 * (y - mean) + k0 with a = gamma*rstd, k1 = -a*rstd*mean(dn*xhat), k0 = -a*mean(dn).
+// EVAL (running statistics are constants, nn.BatchNorm2d in eval()): dy = a * dn.
+template <bool EVAL>
+__global__ void __launch_bounds__(ST_THREADS) bn_bwd_apply_kernel(const bf16* __restrict__ dn, const bf16* __restrict__ y,
+                                                                  const float* __restrict__ red, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  bf16* __restrict__ dy, float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta, unsigned M, int C) {
+  const unsigned cv = C >> 3;
+  const unsigned lanes = ST_THREADS / cv, cvi = threadIdx.x % cv, lane = threadIdx.x / cv;
+  if (lane < lanes) {
+    float a[8], k1[8], k0[8], mu[8];
+    {
+      float g[8], rs[8], r0[8], r1[8];
+      load8f(gamma + cvi * 8, g); load8f(rstd + cvi * 8, rs);
+      if (!EVAL) { load8f(red + cvi * 8, r0); load8f(red + C + cvi * 8, r1); load8f(mean + cvi * 8, mu); }
+      const float invM = 1.0f / static_cast<float>(M);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int ch = c * 8 + t;
-      const float xh = (yv[t] - mean[ch]) * rstd[ch];
-      g[t] = gamma[ch] * rstd[ch] * (g[t] - red[ch] * invM - xh * red[C + ch] * invM);
+      for (int t = 0; t < 8; ++t) {
+        a[t] = g[t] * rs[t];
+        if (!EVAL) { k1[t] = -a[t] * rs[t] * (r1[t] * invM); k0[t] = -a[t] * (r0[t] * invM); }
+      }
     }
-    *reinterpret_cast<bf16x8*>(dy + i * 8) = pack8(g);
-  }
-  if (blockIdx.x == 0 && dgamma) {
-    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) { dgamma[ch] += red[C + ch]; dbeta[ch] += red[ch]; }
-  }
-}
-
-// eval-mode BatchNorm (running statistics are constants): dy = gamma*rstd * dn;  dgamma += sum dn*xhat;  dbeta += sum dn
-__global__ void bn_bwd_apply_eval_kernel(const bf16* __restrict__ dn, const float* __restrict__ red, const float* __restrict__ gamma,
-                                         const float* __restrict__ rstd, bf16* __restrict__ dy, float* __restrict__ dgamma,
-                                         float* __restrict__ dbeta, long long M, int C) {
-  const int cv = C >> 3;
-  const long long total = M * cv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cv);
-    float g[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(dn + i * 8), g);
+    const unsigned step = gridDim.x * lanes;
+    for (unsigned r0 = blockIdx.x * lanes + lane; r0 < M; r0 += 2 * step) {
+      bf16x8 graw[2], yraw[2];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) g[t] *= gamma[c * 8 + t] * rstd[c * 8 + t];
-    *reinterpret_cast<bf16x8*>(dy + i * 8) = pack8(g);
+      for (int u = 0; u < 2; ++u) {
+        const unsigned r = r0 + u * step;
+        if (r < M) {
+          graw[u] = *reinterpret_cast<const bf16x8*>(dn + static_cast<size_t>(r) * C + cvi * 8);
+          if (!EVAL) yraw[u] = *reinterpret_cast<const bf16x8*>(y + static_cast<size_t>(r) * C + cvi * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const unsigned r = r0 + u * step;
+        if (r < M) {
+          float g[8], yv[8];
+          unpack8(graw[u], g);
+          if (!EVAL) {
+            unpack8(yraw[u], yv);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) g[t] = fmaf(a[t], g[t], fmaf(k1[t], yv[t] - mu[t], k0[t]));
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) g[t] *= a[t];
+          }
+          *reinterpret_cast<bf16x8*>(dy + static_cast<size_t>(r) * C + cvi * 8) = pack8(g);
+        }
+      }
+    }
   }
   if (blockIdx.x == 0 && dgamma) {
     for (int ch = threadIdx.x; ch < C; ch += blockDim.x) { dgamma[ch] += red[C + ch]; dbeta[ch] += red[ch]; }
@@ -401,9 +472,16 @@ extern "C" int prismer_im2col_first(const void* in, int in_is_bf16, long long sb
 
 extern "C" int prismer_im2col_nhwc(const void* in, const float* scale, const float* shift, void* out, int B, int H, int W, int C,
                                    int ksz, int stride, int Ho, int Wo, cudaStream_t stream) {
-  if (C % 8 || (ksz != 1 && ksz != 3) || ((scale == nullptr) != (shift == nullptr))) return PRISMER_ERR_SHAPE;
-  im2col_nhwc_kernel<<<blocks_for(static_cast<long long>(B) * Ho * Wo * ksz * ksz * (C / 8), 256), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(in), scale, shift, reinterpret_cast<bf16*>(out), B, H, W, C, ksz, stride, Ho, Wo);
+  if (C % 8 || C / 8 > ST_THREADS || (ksz != 1 && ksz != 3) || ((scale == nullptr) != (shift == nullptr))) return PRISMER_ERR_SHAPE;
+  const long long nslots = static_cast<long long>(B) * Ho * Wo * ksz * ksz;
+  if (nslots <= 0 || nslots >= (1ll << 31) || static_cast<long long>(B) * H * W >= (1ll << 31)) return PRISMER_ERR_SHAPE;
+  const int grid = stem_grid(nslots, C, 2);
+  if (ksz == 3)
+    im2col_nhwc_kernel<3><<<grid, ST_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(in), scale, shift, reinterpret_cast<bf16*>(out), H, W,
+                                                         C, stride, Ho, Wo, static_cast<unsigned>(nslots));
+  else
+    im2col_nhwc_kernel<1><<<grid, ST_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(in), scale, shift, reinterpret_cast<bf16*>(out), H, W,
+                                                         C, stride, Ho, Wo, static_cast<unsigned>(nslots));
   return LAUNCH_CHECK();
 }
 
@@ -425,23 +503,39 @@ extern "C" int prismer_bn_stats(const void* y, float* acc, long long M, int C, c
   return LAUNCH_CHECK();
 }
 
+namespace {
+template <bool EVAL>
+int bn_relu_bwd_launch(const void* dAcol, const void* y, const float* scale, const float* shift, const float* mean, const float* rstd,
+                       const float* gamma, void* dn_scratch, void* dy, float* red, float* dgamma, float* dbeta, int B, int H, int W, int C,
+                       int ksz, int stride, int Ho, int Wo, cudaStream_t stream) {
+  if (C % 8 || C / 8 > ST_THREADS || (ksz != 1 && ksz != 3) || (ksz == 3 && stride != 1 && stride != 2) || (ksz == 1 && stride != 1))
+    return PRISMER_ERR_SHAPE;
+  const long long M = static_cast<long long>(B) * H * W;
+  if (M <= 0 || M >= (1ll << 31) || static_cast<long long>(B) * Ho * Wo >= (1ll << 31)) return PRISMER_ERR_SHAPE;
+  if (cudaMemsetAsync(red, 0, sizeof(float) * 2 * C, stream) != cudaSuccess) return PRISMER_ERR_CUDA;
+  const bf16* dA = reinterpret_cast<const bf16*>(dAcol);
+  const bf16* yy = reinterpret_cast<const bf16*>(y);
+  bf16* dn = reinterpret_cast<bf16*>(dn_scratch);
+  const unsigned npix = static_cast<unsigned>(M);
+  const int grid = stem_grid(M, C, 1);
+  if (ksz == 1)
+    bn_relu_bwd_gather_kernel<1, 1><<<grid, ST_THREADS, 0, stream>>>(dA, yy, scale, shift, mean, rstd, dn, red, H, W, C, Ho, Wo, npix);
+  else if (stride == 2)
+    bn_relu_bwd_gather_kernel<3, 2><<<grid, ST_THREADS, 0, stream>>>(dA, yy, scale, shift, mean, rstd, dn, red, H, W, C, Ho, Wo, npix);
+  else
+    bn_relu_bwd_gather_kernel<3, 1><<<grid, ST_THREADS, 0, stream>>>(dA, yy, scale, shift, mean, rstd, dn, red, H, W, C, Ho, Wo, npix);
+  bn_bwd_apply_kernel<EVAL><<<stem_grid(M, C, 2), ST_THREADS, 0, stream>>>(dn, yy, red, gamma, mean, rstd, reinterpret_cast<bf16*>(dy), dgamma,
+                                                                         dbeta, npix, C);
+  return LAUNCH_CHECK();
+}
+}  // namespace
+
 extern "C" int prismer_bn_relu_bwd(const void* dAcol, const void* y, const float* scale, const float* shift, const float* mean,
                                    const float* rstd, const float* gamma, void* dn_scratch, void* dy, float* red, float* dgamma,
                                    float* dbeta, int B, int H, int W, int C, int ksz, int stride, int Ho, int Wo,
                                    cudaStream_t stream) {
-  if (C % 8 || C / 8 > 256 || (ksz != 1 && ksz != 3)) return PRISMER_ERR_SHAPE;
-  if (cudaMemsetAsync(red, 0, sizeof(float) * 2 * C, stream) != cudaSuccess) return PRISMER_ERR_CUDA;
-  const long long M = static_cast<long long>(B) * H * W;
-  const int lanes = 256 / (C / 8);
-  long long blocks = (M + lanes - 1) / lanes;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_relu_bwd_gather_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(dAcol), reinterpret_cast<const bf16*>(y), scale, shift, mean, rstd,
-      reinterpret_cast<bf16*>(dn_scratch), red, B, H, W, C, ksz, stride, Ho, Wo);
-  bn_bwd_apply_kernel<<<blocks_for(M * (C / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dn_scratch),
-                                                                       reinterpret_cast<const bf16*>(y), red, gamma, mean, rstd,
-                                                                       reinterpret_cast<bf16*>(dy), dgamma, dbeta, M, C);
-  return LAUNCH_CHECK();
+  return bn_relu_bwd_launch<false>(dAcol, y, scale, shift, mean, rstd, gamma, dn_scratch, dy, red, dgamma, dbeta, B, H, W, C, ksz, stride, Ho,
+                                   Wo, stream);
 }
 
 // Same as prismer_bn_relu_bwd for a BatchNorm that ran on its running statistics (module in eval()): nn.BatchNorm2d's eval-mode
@@ -450,18 +544,8 @@ extern "C" int prismer_bn_relu_bwd_eval(const void* dAcol, const void* y, const 
                                         const float* rstd, const float* gamma, void* dn_scratch, void* dy, float* red, float* dgamma,
                                         float* dbeta, int B, int H, int W, int C, int ksz, int stride, int Ho, int Wo,
                                         cudaStream_t stream) {
-  if (C % 8 || C / 8 > 256 || (ksz != 1 && ksz != 3)) return PRISMER_ERR_SHAPE;
-  if (cudaMemsetAsync(red, 0, sizeof(float) * 2 * C, stream) != cudaSuccess) return PRISMER_ERR_CUDA;
-  const long long M = static_cast<long long>(B) * H * W;
-  const int lanes = 256 / (C / 8);
-  long long blocks = (M + lanes - 1) / lanes;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_relu_bwd_gather_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(dAcol), reinterpret_cast<const bf16*>(y), scale, shift, mean, rstd,
-      reinterpret_cast<bf16*>(dn_scratch), red, B, H, W, C, ksz, stride, Ho, Wo);
-  bn_bwd_apply_eval_kernel<<<blocks_for(M * (C / 8), 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dn_scratch), red, gamma, rstd,
-                                                                            reinterpret_cast<bf16*>(dy), dgamma, dbeta, M, C);
-  return LAUNCH_CHECK();
+  return bn_relu_bwd_launch<true>(dAcol, y, scale, shift, mean, rstd, gamma, dn_scratch, dy, red, dgamma, dbeta, B, H, W, C, ksz, stride, Ho,
+                                  Wo, stream);
 }
 
 extern "C" int prismer_conv_weight_pack(const float* w, void* out, int Cout, int Cin, int ksz, int Kpad, cudaStream_t stream) {

@@ -31,6 +31,12 @@ z4 = bf(rows, 3072)
 logits = rn(B * T, 50272)
 labels = torch.randint(3, V, (B, T), device=dev, generator=g)
 act56 = bf(B * 56 * 56, 96)
+# conv-stem layer 1 of a depth / normal / edge stem (vit.py:105-119): y1 [B,112,112,96], consumed by the 3x3 stride-2 conv of layer 2
+y112 = bf(B * 112 * 112, 96)
+dA112 = bf(B * 56 * 56, 9 * 96)
+ch = lambda: (rn(96).abs() + 0.5, rn(96), rn(96), rn(96).abs() + 0.5)
+sc1, sh1, mu1, rs1 = ch()
+gam1 = rn(96)
 # KV-cached decode step kernels (csrc/decode.cu) at the BASE caption-inference shape: weight-streaming skinny GEMMs and single-query attention
 from prismer_b200 import kv_decode  # noqa: E402
 xq = bf(B, Hd)
@@ -50,6 +56,11 @@ CALLS = [
     ("resample_bilinear fp32 [32,64,224,224] -> bf16 NHWC 56x56 (reads every other row pair)", B * 64 * 224 * 224 * 4 // 2 + B * 56 * 56 * 64 * 2,
      lambda: ops.resample_bilinear(lab, 56, 56)),
     ("im2col_nhwc 56x56x96 k3 s2", B * 56 * 56 * 96 * 2 + B * 28 * 28 * 9 * 96 * 2, lambda: ops.im2col_nhwc(act56, B, 56, 56, 96, 3, 2)),
+    ("im2col_nhwc 112x112x96 k3 s2 + BN affine + ReLU on load", B * 112 * 112 * 96 * 2 + B * 56 * 56 * 9 * 96 * 2,
+     lambda: ops.im2col_nhwc(y112, B, 112, 112, 96, 3, 2, sc1, sh1)),
+    ("bn_relu_bwd 112x112x96 under a k3 s2 conv: gather (dAcol + y -> dn) and apply (dn + y -> dy), two launches",
+     (B * 56 * 56 * 9 * 96 + 5 * B * 112 * 112 * 96) * 2,
+     lambda: ops.bn_relu_bwd(dA112, y112, sc1, sh1, mu1, rs1, gam1, None, None, B, 112, 112, 96, 3, 2, 56, 56)),
     ("ce_loss_fwd [960,50265] fp32", B * T * V * 4, lambda: ops.ce_loss_fwd(logits, labels, V)),
     ("skinny_linear [32,768]x[3072,768] gelu (decode MLP fc: weights streamed once)", 3072 * Hd * 2, lambda: kv_decode.skinny_linear(xq, w_fc, b_fc, act="gelu")),
     ("skinny_linear [32,768]x[768,768] + residual, then ln_fwd on the 32 rows", Hd * Hd * 2,
