@@ -15,6 +15,7 @@ batch-first rows ``r = b*T + t``; the decoder reads the encoder output in place 
 from __future__ import annotations
 
 import math
+import os
 import random
 from types import SimpleNamespace
 from typing import Dict, List, Optional
@@ -280,6 +281,35 @@ def _off_critical_path(fn, *tensors):
         sd.run(fn, *tensors)
 
 
+# The six expert stems (vit.py:88-120) are independent of each other until their tokens are assembled, and their deeper layers are
+# sub-wave kernels (14 x 14 / 28 x 28 grids): each stem's forward / backward chain is enqueued on its own stream -- parallel branches of
+# the captured graph -- forked from and joined back into the calling stream.  Tensors a branch allocates are consumed on the calling
+# stream only after the join, and a branch stream starts its next use by waiting on the calling stream, so block reuse stays ordered.
+STEM_BRANCHES = os.environ.get("PRISMER_STEM_BRANCHES", "1") != "0"      # A/B switch
+_branch_streams = {}
+
+
+def _fork(dev, i: int):
+    key = (str(dev), i)
+    s = _branch_streams.get(key)
+    if s is None:
+        s = _branch_streams[key] = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    return s
+
+
+def _join(dev, streams):
+    if not streams:
+        return
+    main = torch.cuda.current_stream(dev)
+    for s in streams:
+        main.wait_stream(s)
+
+
+def _branching(dev, domains) -> bool:
+    return STEM_BRANCHES and SIDE_STREAM and dev.type == "cuda" and len(set(domains)) == len(domains) and len(domains) > 1
+
+
 def _wgrad(dy2d, x2d, wg):
     """wg[N_out, K_in] (fp32) += dy^T . x   (both operands MN-major: no transposes materialised)."""
     if wg is not None:
@@ -477,11 +507,19 @@ def encoder_forward(vit, experts: Dict, save: bool, inst_table: Optional[torch.T
 
     if has_res:
         toks = []
-        for e in names:
-            domain = "seg" if "seg" in e else e
+        domains = ["seg" if "seg" in e else e for e in names]
+        branch = _branching(dev, domains)
+        forks = []
+        for i, (e, domain) in enumerate(zip(names, domains)):
             xin = experts[e]["label"] if e == "obj_detection" else experts[e]
-            t, gh, gw, ssv = _stem_fwd(vit.conv1[domain], xin, training, save)
+            if branch:
+                forks.append(_fork(dev, i))
+                with torch.cuda.stream(forks[-1]):
+                    t, gh, gw, ssv = _stem_fwd(vit.conv1[domain], xin, training, save)
+            else:
+                t, gh, gw, ssv = _stem_fwd(vit.conv1[domain], xin, training, save)
             toks.append((e, domain, t, gh, gw, ssv))
+        _join(dev, forks)
         N = sum(gh * gw for _, _, _, gh, gw, _ in toks)
         xf = torch.empty((N * B, D), dtype=BF16, device=dev)
         off = 0
@@ -547,14 +585,25 @@ def encoder_backward(vit, sv, dout):
     uniform = all(m.n == sv.mods[0].n for m in sv.mods)
     if pos_tr and uniform:
         _pos_grad(vit, dxf, B, sv.mods[0].n, D, len(sv.mods), sv.mods[0].n, sv.mods[0].interp)
-    for m in sv.mods:
+    branch = _branching(dx0.device, [m.domain for m in sv.mods])
+    forks = []
+    for i, m in enumerate(sv.mods):
         dt = dxf[m.off * B:(m.off + m.n) * B]
         if pos_tr and not uniform:
-            _pos_grad(vit, dt, B, m.n, D, 1, 0, m.interp)
-        dsrc = torch.empty((B * m.n, D), dtype=BF16, device=dx0.device)
-        ops.assemble_tokens_bwd(dt, D, B * D, dsrc, B, m.n, D, m.gh, m.gw, m.inst, m.table,
-                                ie._g32 if (m.inst is not None and ie.requires_grad) else None)
-        _stem_bwd(vit.conv1[m.domain], m.stem, dsrc)
+            _pos_grad(vit, dt, B, m.n, D, 1, 0, m.interp)           # shared table: stays on the calling stream
+        if branch:
+            forks.append(_fork(dx0.device, i))
+            with torch.cuda.stream(forks[-1]):
+                dsrc = torch.empty((B * m.n, D), dtype=BF16, device=dx0.device)    # allocated on the branch: its block is only reused there
+                ops.assemble_tokens_bwd(dt, D, B * D, dsrc, B, m.n, D, m.gh, m.gw, m.inst, m.table,
+                                        ie._g32 if (m.inst is not None and ie.requires_grad) else None)
+                _stem_bwd(vit.conv1[m.domain], m.stem, dsrc)
+        else:
+            dsrc = torch.empty((B * m.n, D), dtype=BF16, device=dx0.device)
+            ops.assemble_tokens_bwd(dt, D, B * D, dsrc, B, m.n, D, m.gh, m.gw, m.inst, m.table,
+                                    ie._g32 if (m.inst is not None and ie.requires_grad) else None)
+            _stem_bwd(vit.conv1[m.domain], m.stem, dsrc)
+    _join(dx0.device, forks)
 
 
 def _pos_grad(vit, dtok_sf, B, n_tok, D, n_slots, slot_stride, interp):
