@@ -163,31 +163,58 @@ __global__ void assemble_kernel(const bf16* __restrict__ src, const bf16* __rest
   }
 }
 
-// backward of the assembly for one modality: dsrc[b*n_tok+n,:] = ddst[b,n,:]; dinst_emb[row] += ddst rows (atomics)
-__global__ void assemble_bwd_kernel(const bf16* __restrict__ ddst, long long ddst_bs, long long ddst_rs, bf16* __restrict__ dsrc,
-                                    const long long* __restrict__ inst, const int* __restrict__ table,
-                                    float* __restrict__ dinst_emb, int B, int n_tok, int D, int gh, int gw, int Hi, int Wi) {
-  const int vpr = D >> 3;
-  const long long total = static_cast<long long>(B) * n_tok * vpr;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % vpr);
-    const long long rn = i / vpr;
-    const int n = static_cast<int>(rn % n_tok), b = static_cast<int>(rn / n_tok);
-    const bf16x8 v = *reinterpret_cast<const bf16x8*>(ddst + b * ddst_bs + static_cast<long long>(n) * ddst_rs + c * 8);
-    *reinterpret_cast<bf16x8*>(dsrc + rn * D + c * 8) = v;
-    if (inst && dinst_emb) {
-      const int y = n / gw, x = n % gw;
-      const int sy = min(static_cast<int>(floorf(y * (static_cast<float>(Hi) / gh))), Hi - 1);
-      const int sx = min(static_cast<int>(floorf(x * (static_cast<float>(Wi) / gw))), Wi - 1);
-      const long long id = inst[(static_cast<long long>(b) * Hi + sy) * Wi + sx];
-      const int row = table[id & 255];
-      if (row >= 0) {
-        float f[8]; unpack8(v, f);
+// backward of the assembly for one modality: dsrc[b*n_tok+n,:] = ddst[b,n,:]   (a strided row copy)
+__global__ void assemble_bwd_kernel(const bf16* __restrict__ ddst, long long ddst_bs, long long ddst_rs, bf16* __restrict__ dsrc, int B,
+                                    int n_tok, int D) {
+  const unsigned vpr = D >> 3;
+  const unsigned total = static_cast<unsigned>(B) * n_tok * vpr;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c = i % vpr, rn = i / vpr, n = rn % n_tok, b = rn / n_tok;
+    *reinterpret_cast<bf16x8*>(dsrc + static_cast<size_t>(rn) * D + c * 8) =
+        *reinterpret_cast<const bf16x8*>(ddst + b * ddst_bs + static_cast<long long>(n) * ddst_rs + c * 8);
+  }
+}
+
+// dinst_emb[table[inst(b, nearest(n))], :] += ddst[b, n, :]   (vit.py:147-150: the instance embedding added to the object-detection tokens).
+// B * n_tok token rows scatter into the few table rows a batch uses (<= 128): one global atomic per element (the first version) puts
+// hundreds of same-address atomics in a row.  Here a block owns IE_CH channels and a slice of the tokens, accumulates its
+// [IE_ROWS x IE_CH] slab in shared memory and flushes only the non-zero entries.
+constexpr int IE_ROWS = 128, IE_CH = 32, IE_THREADS = 256;
+__global__ void __launch_bounds__(IE_THREADS) inst_emb_grad_kernel(const bf16* __restrict__ ddst, long long ddst_bs, long long ddst_rs,
+                                                                   const long long* __restrict__ inst, const int* __restrict__ table,
+                                                                   float* __restrict__ dinst_emb, int B, int n_tok, int D, int gh, int gw,
+                                                                   int Hi, int Wi) {
+  __shared__ float slab[IE_ROWS * IE_CH];
+  for (int i = threadIdx.x; i < IE_ROWS * IE_CH; i += IE_THREADS) slab[i] = 0.f;
+  __syncthreads();
+  const int c0 = blockIdx.x * IE_CH;                       // first channel of this block
+  const int cvi = threadIdx.x & 3, lane = threadIdx.x >> 2; // 4 channel vectors x 64 token lanes
+  const int ntok = B * n_tok;
+  const bool live = c0 + cvi * 8 < D;
+  for (int tk = blockIdx.y * (IE_THREADS / 4) + lane; tk < ntok; tk += gridDim.y * (IE_THREADS / 4)) {
+    const int n = tk % n_tok, b = tk / n_tok;
+    const int y = n / gw, x = n % gw;
+    // nearest (legacy): src = floor(dst * in/out), as in assemble_kernel
+    const int sy = min(static_cast<int>(floorf(y * (static_cast<float>(Hi) / gh))), Hi - 1);
+    const int sx = min(static_cast<int>(floorf(x * (static_cast<float>(Wi) / gw))), Wi - 1);
+    const long long id = inst[(static_cast<long long>(b) * Hi + sy) * Wi + sx];
+    const int row = table[id & 255];
+    if (row < 0 || !live) continue;
+    float f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(ddst + b * ddst_bs + static_cast<long long>(n) * ddst_rs + c0 + cvi * 8), f);
+    if (row < IE_ROWS) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) atomicAdd(dinst_emb + static_cast<long long>(row) * D + c * 8 + t, f[t]);
-      }
+      for (int t = 0; t < 8; ++t) atomicAdd(&slab[row * IE_CH + cvi * 8 + t], f[t]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) atomicAdd(dinst_emb + static_cast<long long>(row) * D + c0 + cvi * 8 + t, f[t]);
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < IE_ROWS * IE_CH; i += IE_THREADS) {
+    const float v = slab[i];
+    const int row = i / IE_CH, ch = c0 + i % IE_CH;
+    if (v != 0.f && ch < D) atomicAdd(dinst_emb + static_cast<long long>(row) * D + ch, v);
   }
 }
 
@@ -339,9 +366,17 @@ extern "C" int prismer_assemble_tokens_bwd(const void* ddst, long long ddst_bs, 
                                            cudaStream_t stream) {
   if (D % 8 || gh * gw != n_tok) return PRISMER_ERR_SHAPE;
   const long long total = static_cast<long long>(B) * n_tok * (D / 8);
-  assemble_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(ddst), ddst_bs, ddst_rs, reinterpret_cast<bf16*>(dsrc), reinterpret_cast<const long long*>(inst), table,
-      dinst_emb, B, n_tok, D, gh, gw, Hi, Wi);
+  if (total >= (1ll << 31)) return PRISMER_ERR_SHAPE;
+  assemble_bwd_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(ddst), ddst_bs, ddst_rs,
+                                                                  reinterpret_cast<bf16*>(dsrc), B, n_tok, D);
+  if (inst && dinst_emb) {
+    const int ntok = B * n_tok;
+    int ysplit = (ntok + 64 * 16 - 1) / (64 * 16);          // >= 16 tokens per thread before another slice of the tokens pays
+    ysplit = ysplit < 1 ? 1 : (ysplit > 16 ? 16 : ysplit);
+    inst_emb_grad_kernel<<<dim3((D + IE_CH - 1) / IE_CH, ysplit), IE_THREADS, 0, stream>>>(
+        reinterpret_cast<const bf16*>(ddst), ddst_bs, ddst_rs, reinterpret_cast<const long long*>(inst), table, dinst_emb, B, n_tok, D, gh,
+        gw, Hi, Wi);
+  }
   return LAUNCH_CHECK();
 }
 

@@ -91,33 +91,39 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
 
 // ---------------------------------------------------------------------------------------------- im2col
 // First layer: generic strided fp32 / bf16 input with few channels (1 or 3); K = k*k*Cin padded to Kpad; per-element gather.
-__global__ void im2col_first_kernel(const void* __restrict__ in, int in_is_bf16, long long sb, long long sc, long long sy,
-                                    long long sx, bf16* __restrict__ out, int B, int Cin, int H, int W, int ksz, int stride,
-                                    int Ho, int Wo, int Kpad) {
+// The (c, kh, kw) decomposition of the <= 64 K indices comes from a small shared-memory table instead of three divisions per element;
+// index arithmetic is 32-bit (the input is a few MB and stays in L2, the kernel is bound by its 13-26 MB of output).
+__global__ void __launch_bounds__(256) im2col_first_kernel(const void* __restrict__ in, int in_is_bf16, long long sb, long long sc,
+                                                           long long sy, long long sx, bf16* __restrict__ out, int B, int Cin, int H, int W,
+                                                           int ksz, int stride, int Ho, int Wo, int Kpad) {
+  __shared__ int lut[64];                       // k -> c | kh << 8 | kw << 16, or -1 for the zero padding columns
   const int pad = ksz == 3 ? 1 : 0;
-  const int K = ksz * ksz * Cin, kv = Kpad >> 3;
-  const long long total = static_cast<long long>(B) * Ho * Wo * kv;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int kc = static_cast<int>(i % kv);
-    const long long row = i / kv;
-    const int xo = static_cast<int>(row % Wo), yo = static_cast<int>((row / Wo) % Ho), b = static_cast<int>(row / (static_cast<long long>(Wo) * Ho));
+  const int K = ksz * ksz * Cin;
+  const unsigned kv = Kpad >> 3;
+  for (int k = threadIdx.x; k < 64; k += blockDim.x)
+    lut[k] = (k < K) ? ((k % Cin) | ((k / (Cin * ksz)) << 8) | (((k / Cin) % ksz) << 16)) : -1;
+  __syncthreads();
+  const unsigned total = static_cast<unsigned>(B) * Ho * Wo * kv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned kc = i % kv, row = i / kv;
+    const unsigned xo = row % Wo, t2 = row / Wo, yo = t2 % Ho, b = t2 / Ho;
+    const int y0 = static_cast<int>(yo) * stride - pad, x0 = static_cast<int>(xo) * stride - pad;
+    const long long base = b * sb;
     float v[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-      const int k = kc * 8 + t;
+      const int e = lut[kc * 8 + t];
       float val = 0.f;
-      if (k < K) {
-        const int c = k % Cin, kw = (k / Cin) % ksz, kh = k / (Cin * ksz);
-        const int yi = yo * stride - pad + kh, xi = xo * stride - pad + kw;
+      if (e >= 0) {
+        const int c = e & 255, yi = y0 + ((e >> 8) & 255), xi = x0 + (e >> 16);
         if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
-          const long long off = b * sb + c * sc + yi * sy + xi * sx;
-          val = in_is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(in)[off]) : reinterpret_cast<const float*>(in)[off];
+          const long long off = base + c * sc + yi * sy + xi * sx;
+          val = in_is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(in)[off]) : __ldg(reinterpret_cast<const float*>(in) + off);
         }
       }
       v[t] = val;
     }
-    *reinterpret_cast<bf16x8*>(out + row * Kpad + kc * 8) = pack8(v);
+    *reinterpret_cast<bf16x8*>(out + static_cast<size_t>(row) * Kpad + kc * 8) = pack8(v);
   }
 }
 
@@ -186,33 +192,39 @@ __global__ void __launch_bounds__(ST_THREADS) im2col_nhwc_kernel(const bf16* __r
 }
 
 // ---------------------------------------------------------------------------------------------- BatchNorm statistics
-// y bf16 [M, C]: acc[0][c] += sum, acc[1][c] += sum of squares (acc must be zeroed by the caller)
-__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ y, float* __restrict__ acc, long long M, int C,
-                                                       int rows_per_block) {
-  // thread -> (channel vector cvi, row lane); blockDim.x = 256
-  const int cv = C >> 3;
-  const int lanes = 256 / cv > 0 ? 256 / cv : 1;       // row lanes per block when cv <= 256
-  const int cvi = threadIdx.x % cv, rl = threadIdx.x / cv;
-  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
-  const long long r1 = min(M, r0 + rows_per_block);
-  __shared__ float red[2][2048];   // [sum | sumsq][lane * C + channel]; lanes * C <= 2048
-  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (rl < lanes) {
-    for (long long r = r0 + rl; r < r1; r += lanes) {
-      float f[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(y + r * C + cvi * 8), f);
+// y bf16 [M, C]: acc[0][c] += sum, acc[1][c] += sum of squares (acc must be zeroed by the caller).  Same (lanes x channel-vector)
+// thread layout as the kernels above; four independent 16-byte row loads in flight per thread.
+__global__ void __launch_bounds__(ST_THREADS) bn_stats_kernel(const bf16* __restrict__ y, float* __restrict__ acc, unsigned M, int C) {
+  const unsigned cv = C >> 3;
+  const unsigned lanes = ST_THREADS / cv, cvi = threadIdx.x % cv, lane = threadIdx.x / cv;
+  __shared__ float red[2][ST_THREADS * 8];   // [sum | sumsq][lane * C + channel]; lanes * C <= 3072
+  if (lane < lanes) {
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned step = gridDim.x * lanes;
+    for (unsigned r0 = blockIdx.x * lanes + lane; r0 < M; r0 += 4 * step) {
+      bf16x8 raw[4];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) { s[t] += f[t]; q[t] += f[t] * f[t]; }
+      for (int u = 0; u < 4; ++u) {
+        const unsigned r = r0 + u * step;
+        raw[u] = r < M ? *reinterpret_cast<const bf16x8*>(y + static_cast<size_t>(r) * C + cvi * 8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { s[t] += f[t]; q[t] = fmaf(f[t], f[t], q[t]); }
+      }
     }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { red[0][rl * C + cvi * 8 + t] = s[t]; red[1][rl * C + cvi * 8 + t] = q[t]; }
+    for (int t = 0; t < 8; ++t) { red[0][lane * C + cvi * 8 + t] = s[t]; red[1][lane * C + cvi * 8 + t] = q[t]; }
   }
   __syncthreads();
-  // one atomic per channel per block (instead of one per thread): 20x fewer same-address atomics
+  // one atomic per channel per block
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
     const int which = c / C, ch = c % C;
     float a = 0.f;
-    for (int l = 0; l < lanes; ++l) a += red[which][l * C + ch];
+    for (unsigned l = 0; l < lanes; ++l) a += red[which][l * C + ch];
     atomicAdd(acc + which * C + ch, a);
   }
 }
@@ -464,9 +476,11 @@ extern "C" int prismer_resample_bilinear(const float* x, void* out, int B, int C
 extern "C" int prismer_im2col_first(const void* in, int in_is_bf16, long long sb, long long sc, long long sy, long long sx,
                                     void* out, int B, int Cin, int H, int W, int ksz, int stride, int Ho, int Wo, int Kpad,
                                     cudaStream_t stream) {
-  if (Kpad % 8 || Kpad < ksz * ksz * Cin || (ksz != 1 && ksz != 3)) return PRISMER_ERR_SHAPE;
-  im2col_first_kernel<<<blocks_for(static_cast<long long>(B) * Ho * Wo * (Kpad / 8), 256), 256, 0, stream>>>(
-      in, in_is_bf16, sb, sc, sy, sx, reinterpret_cast<bf16*>(out), B, Cin, H, W, ksz, stride, Ho, Wo, Kpad);
+  if (Kpad % 8 || Kpad > 64 || Kpad < ksz * ksz * Cin || (ksz != 1 && ksz != 3)) return PRISMER_ERR_SHAPE;
+  const long long total = static_cast<long long>(B) * Ho * Wo * (Kpad / 8);
+  if (total <= 0 || total >= (1ll << 31)) return PRISMER_ERR_SHAPE;
+  im2col_first_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(in, in_is_bf16, sb, sc, sy, sx, reinterpret_cast<bf16*>(out), B, Cin, H, W,
+                                                                 ksz, stride, Ho, Wo, Kpad);
   return LAUNCH_CHECK();
 }
 
@@ -488,15 +502,10 @@ extern "C" int prismer_im2col_nhwc(const void* in, const float* scale, const flo
 extern "C" int prismer_bn_stats(const void* y, float* acc, long long M, int C, const float* gamma, const float* beta,
                                 float* running_mean, float* running_var, float* scale, float* shift, float* mean, float* rstd,
                                 float eps, float momentum, int training, cudaStream_t stream) {
-  if (C % 8 || C / 8 > 256) return PRISMER_ERR_SHAPE;
+  if (C % 8 || C / 8 > ST_THREADS || M <= 0 || M >= (1ll << 31)) return PRISMER_ERR_SHAPE;
   if (training) {
     if (cudaMemsetAsync(acc, 0, sizeof(float) * 2 * C, stream) != cudaSuccess) return PRISMER_ERR_CUDA;
-    const int lanes = 256 / (C / 8);
-    long long rpb = (M + 148 * 4 - 1) / (148 * 4);
-    rpb = ((rpb + lanes - 1) / lanes) * lanes;
-    if (rpb < lanes) rpb = lanes;
-    const int grid = static_cast<int>((M + rpb - 1) / rpb);
-    bn_stats_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(y), acc, M, C, static_cast<int>(rpb));
+    bn_stats_kernel<<<stem_grid(M, C, 4), ST_THREADS, 0, stream>>>(reinterpret_cast<const bf16*>(y), acc, static_cast<unsigned>(M), C);
   }
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(acc, gamma, beta, running_mean, running_var, scale, shift, mean, rstd, M, C,
                                                          eps, momentum, training);
