@@ -759,11 +759,12 @@ def cross_kv(dec, enc):
 
 
 def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: bool, need_logits: bool = True,
-                    kv: Optional[SimpleNamespace] = None, last_only: bool = False, enc_repeat: int = 1):
+                    kv: Optional[SimpleNamespace] = None, last_only: bool = False, enc_repeat: int = 1, kv_sink=None):
     """RobertaForCausalLMModified.forward (roberta.py:358-399) on a batch of pre-tokenised ids.
     ``kv``: precomputed ``cross_kv``; ``last_only``: LM head on the last position of every row only (greedy decoding);
     ``enc_repeat`` = k (inference only): ``input_ids`` holds k consecutive rows per image and ``enc`` ONE row per image -- the visual
-    K/V are projected once per image and shared by its k candidates (rank inference without ``tile``, prismer_caption.py:94-96)."""
+    K/V are projected once per image and shared by its k candidates (rank inference without ``tile``, prismer_caption.py:94-96);
+    ``kv_sink(li, qkv3)``: called with every self-attention layer's fused projection [B, T, 3H] (KV-cache prefill, kv_decode.py)."""
     cfg = dec.config
     st = _store(dec)
     training = dec.training
@@ -793,7 +794,7 @@ def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: 
     assert Be * enc_repeat == B and (enc_repeat == 1 or not save), "encoder_hidden_states batch mismatch"
     sv.enc_flat, sv.kv_all, sv.S, sv.enc_bs, sv.enc_rs = enc_flat, kv_all, S, ebs, ers_
     for li, (layer, cross, adp) in enumerate(encoder.layer):
-        h, lsv = _dec_self_fwd(layer, h, B, T, nh, attention_mask, p_h, p_a, seed, li, save)
+        h, lsv = _dec_self_fwd(layer, h, B, T, nh, attention_mask, p_h, p_a, seed, li, save, kv_sink)
         # cross attention over the visual tokens (roberta.py:225; no mask)
         q = gemm(h, cross.self.query.weight._c16, bias=cross.self.query.bias.data)
         k3 = _x3(kv_all, Be, S, ebs, ers_, li * 2 * Hd, li * 2 * Hd + Hd)
@@ -813,7 +814,7 @@ def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: 
                                         mua=mua, rsa=rsa, h_a=h_a)
             lsv.mlp = msv
             sv.layers.append(lsv)
-    h, osv = _dec_self_fwd(encoder.output_layer, h, B, T, nh, attention_mask, p_h, p_a, seed, L, save)
+    h, osv = _dec_self_fwd(encoder.output_layer, h, B, T, nh, attention_mask, p_h, p_a, seed, L, save, kv_sink)
     h, omsv = _dec_mlp_fwd(encoder.output_layer, h, p_h, seed, L, save)
     sv.out_self, sv.out_mlp = osv, omsv
     if not need_logits:
@@ -839,12 +840,14 @@ def decoder_forward(dec, input_ids, attention_mask, enc, labels, weights, save: 
     return logits, loss_samples, loss_mean, sv
 
 
-def _dec_self_fwd(layer, h, B, T, nh, mask, p_h, p_a, seed, li, save):
+def _dec_self_fwd(layer, h, B, T, nh, mask, p_h, p_a, seed, li, save, kv_sink=None):
     at = layer.attention
     Hd = h.shape[1]
     grp = at.self._grp
     qkv = gemm(h, grp.w16, bias=grp.b)                                            # fused q/k/v projection
     q3 = qkv.view(B, T, 3 * Hd)
+    if kv_sink is not None:
+        kv_sink(li, q3)
     o = torch.empty((B * T, Hd), dtype=BF16, device=h.device)
     _, lse = ops.attention_fwd(q3[..., :Hd], q3[..., Hd:2 * Hd], q3[..., 2 * Hd:], nh, causal=True, key_mask=mask, drop_p=p_a,
                                seed=seed, rng_stream=_site(_RS_SELF_P, li), need_lse=save, out=o.view(B, T, Hd))

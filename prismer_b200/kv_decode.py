@@ -51,6 +51,8 @@ def decode_attention(q, k, v, kv_bs, kv_rs, length, heads, *, k_new=None, v_new=
 # Independent batch slices decoded concurrently on separate streams (parallel branches of the captured graph).  Measured on B200 at B = 32:
 # 1 chain 30.7 ms per batch, 2 chains 31.8, 4 chains 34.5, 8 chains 58 -- the branches do not overlap usefully, so the default is ONE chain.
 DECODE_CHAINS = 1
+# The prompt is fed in one full-sequence pass that also fills the caches (KVDecoder.prefill); False = token by token through the step kernels.
+PREFILL = True
 _chain_streams = {}
 
 
@@ -89,6 +91,20 @@ class KVDecoder:
         f = skinny_linear(h, layer.intermediate.dense.weight._c16, layer.intermediate.dense.bias.data, act="gelu")
         _, h1 = skinny_linear(f, layer.output.dense.weight._c16, layer.output.dense.bias.data, residual=h, ln=layer.output.LayerNorm)
         return h1
+
+    def prefill(self, prompt_ids: torch.Tensor):
+        """All T0 prompt positions in ONE pass of the full-sequence decoder forward (``engine.decoder_forward``: causal + prompt mask,
+        the tcgen05 GEMMs over B*T0 rows), whose per-layer fused q/k/v projections fill the caches; returns the fp32 logits [B, V] of the
+        last prompt position.  Replaces T0 single-token passes (3 of the 19 passes of a BASE caption: ~190 launches each)."""
+        Hd, T0 = self.Hd, prompt_ids.shape[1]
+
+        def sink(li, qkv3):
+            self.kc[li][:, :T0].copy_(qkv3[..., Hd:2 * Hd])
+            self.vc[li][:, :T0].copy_(qkv3[..., 2 * Hd:])
+
+        logits, _, _, _ = engine.decoder_forward(self.dec, prompt_ids, self.mask[:, :T0].contiguous(), None, None, None, save=False,
+                                                 kv=self.kv, last_only=True, kv_sink=sink)
+        return logits
 
     def step(self, ids_so_far: torch.Tensor, need_logits: bool = True):
         """Feed the token at position t = ids_so_far.shape[1] - 1 (ids_so_far: [B, t+1] int64, contiguous); returns the fp32 logits
@@ -130,8 +146,11 @@ def _chain(dec, ids, T0, kv, lo, hi, max_length, min_length, early_exit, steps, 
     st = KVDecoder(dec, kv, lo, hi, max_length, prompt_mask)
     unfinished = torch.ones(hi - lo, dtype=torch.int64, device=ids.device)
     last = None
-    for t in range(T0):
-        last = st.step(ids[:, :t + 1].contiguous(), need_logits=(t == T0 - 1))
+    if PREFILL and T0 > 1 and lo == 0 and hi == kv.B:
+        last = st.prefill(ids[:, :T0].contiguous())
+    else:
+        for t in range(T0):
+            last = st.step(ids[:, :t + 1].contiguous(), need_logits=(t == T0 - 1))
     cur = T0
     while cur < max_length:
         tok = ops.argmax(last, V, suppress_eos=cur < min_length, eos=eos)
@@ -148,8 +167,8 @@ def _chain(dec, ids, T0, kv, lo, hi, max_length, min_length, early_exit, steps, 
 
 
 def greedy_loop(dec, ids, T0, enc, max_length, min_length, early_exit, steps=None, prompt_mask=None, chains=None):
-    """KV-cached counterpart of ``generation._greedy_loop_nocache`` (same contract): the prompt is fed token by token (filling the
-    caches), then one token per step.  With ``early_exit=False`` there is no host synchronisation, so the loop can be captured in a
+    """KV-cached counterpart of ``generation._greedy_loop_nocache`` (same contract): the prompt goes through one full-sequence pass that
+    fills the caches (``KVDecoder.prefill``), then one token per step.  With ``early_exit=False`` there is no host synchronisation, so the loop can be captured in a
     CUDA graph.  Optionally (``chains`` / ``DECODE_CHAINS`` > 1) the batch is split into slices decoded on separate streams (parallel
     branches of the graph); measured on B200 this does not pay (see DECODE_CHAINS), so one chain is the default."""
     B = ids.shape[0]
