@@ -431,7 +431,10 @@ def decode_bytes(model, B, S, T0, max_length):
     head = dec.roberta.embeddings.word_embeddings.weight.numel() + sum(p.numel() for n, p in dec.lm_head.named_parameters() if "decoder" not in n)
     xkv_w = sum(p.numel() for l in dec.roberta.encoder.layer for p in (l[1].self.key.weight, l[1].self.value.weight))   # used once per call
     body = sum(p.numel() for p in dec.roberta.encoder.parameters()) - xkv_w
-    passes, head_passes = max_length - 1, max_length - T0
+    from prismer_b200 import generation, kv_decode
+    # the prompt's T0 positions are one (full-sequence) pass when the caches are prefilled, T0 single-token passes otherwise
+    prefilled = generation.KV_CACHE and kv_decode.PREFILL and T0 > 1
+    passes, head_passes = (max_length - T0 if prefilled else max_length - 1), max_length - T0
     cross = L * B * S * Hd * 2
     return 2 * (passes * (body + cross) + head_passes * head)
 
@@ -542,7 +545,8 @@ def run_caption(args, model, ex_h, ex_d, dev, rank, world, h2d, compact, steps=N
                 "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": None,
                 "algorithmic_bytes_per_batch": nbytes_dec, "decode_ms_per_batch": round(dec_ms, 3), "encoder_ms_per_batch": round(enc_ms, 3),
                 "encoder_tflops": round(85.2 * B / enc_ms, 1), "peak_source": pk["source"] + " copy bandwidth",
-                "note": "bytes = 19 decoder passes x (body weights + projected visual K/V of the batch) + 16 LM-head passes (SURVEY 8d config 2); "
+                "note": "bytes = decoder passes (1 prompt prefill + 15 single-token steps; 19 without prefill) x (body weights + projected visual "
+                        "K/V of the batch) + 16 LM-head passes (SURVEY 8d config 2); "
                         "decode time = graphed batch time - graphed encoder-only time"}
     return {"metric": "Prismer-BASE greedy captions/sec", "value": round(world * B / (float(t) / 1e3), 2), "unit": "captions/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(float(t), 3),

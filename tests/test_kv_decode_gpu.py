@@ -139,9 +139,13 @@ def test_graphed_captioner_multi_chain_equals_single_chain():
     random.seed(2)
     got = cap().clone()
     random.seed(2)                                           # same instance-embedding draw as the replay above
-    with torch.no_grad():
-        enc = m.expert_encoder(ex).transpose(0, 1)
-        want = m.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=12, min_length=6)
+    kv_decode.PREFILL = False                                # the slices feed the prompt token by token: compare like with like
+    try:
+        with torch.no_grad():
+            enc = m.expert_encoder(ex).transpose(0, 1)
+            want = m.text_decoder.generate(input_ids=prefix, encoder_hidden_states=enc, num_beams=1, max_length=12, min_length=6)
+    finally:
+        kv_decode.PREFILL = True
     torch.cuda.synchronize()
     got = generation.trim_finished(got, 4, TINY_DEC["eos_token_id"])
     L = min(got.shape[1], want.shape[1])
