@@ -74,6 +74,13 @@ class ParamStore:
         for n, p in named:
             if id(p) in dec_ids:
                 add(p)
+        # ... and the expert stems + instance embedding last: theirs are the final gradients of the backward, so everything before them
+        # can be reduced while the stems' backward runs (three-segment overlap)
+        late_ids = {id(p) for n, p in named if id(p) not in dec_ids and
+                    ("instance_embedding" in n or (".conv1." in "." + n and ".conv1.rgb." not in "." + n))}
+        for n, p in named:
+            if id(p) not in late_ids:
+                add(p)
         for n, p in named:
             add(p)
         self._dec_ids = dec_ids
@@ -98,9 +105,12 @@ class ParamStore:
         self.grad_t = torch.zeros(max(t_n, 8), dtype=F32, device=device)
         self.n_train = t_n
         self.n_train_dec = 0
+        self.n_train_late = t_n                    # start of the (stems + instance embedding) tail of the trainable buffers
         for p, o in zip(self.train_params, t_offs):
             if id(p) in dec_ids:
                 self.n_train_dec = o + (p.numel() + 7) // 8 * 8
+            if id(p) in late_ids:
+                self.n_train_late = min(self.n_train_late, o)
         self._offset = {}
         for ps, offs, master, c16, trainable in ((self.train_params, t_offs, self.master_t, self.c16_t, True),
                                                  (self.frozen_params, f_offs, self.master_f, self.c16_f, False)):
@@ -551,8 +561,9 @@ def encoder_forward(vit, experts: Dict, save: bool, inst_table: Optional[torch.T
     return out, S, B, sv
 
 
-def encoder_backward(vit, sv, dout):
-    """dout: [S*B, D] gradient wrt the encoder output (seq-first rows)."""
+def encoder_backward(vit, sv, dout, defer_stems: bool = False):
+    """dout: [S*B, D] gradient wrt the encoder output (seq-first rows).  ``defer_stems``: stop before the expert stems and return the
+    token gradient ``encoder_backward_stems`` needs (every gradient except the stems' and the instance embedding's is final by then)."""
     B, S, P, D = sv.B, sv.S, sv.P, vit.width
     x, mu, rs = sv.post
     dx, _ = _ln_bwd(dout, x, mu, rs, vit.ln_post)
@@ -578,19 +589,30 @@ def encoder_backward(vit, sv, dout):
     if pos_tr:
         _pos_grad(vit, dtok, B, P, D, 1, 0, None)
     if not sv.names:
-        return
+        return None
     dxf = _resampler_bwd(vit.resampler, sv.res, dx0[P * B:], sv.xf, B, sv.N)      # [N*B, D]
-    ie = getattr(vit, "instance_embedding", None)
     # all expert modalities share the positional embedding: one reduction over batch and modality slots when uniform
     uniform = all(m.n == sv.mods[0].n for m in sv.mods)
     if pos_tr and uniform:
         _pos_grad(vit, dxf, B, sv.mods[0].n, D, len(sv.mods), sv.mods[0].n, sv.mods[0].interp)
+    elif pos_tr:
+        for m in sv.mods:                                            # shared table: on the calling stream, before the stem branches
+            _pos_grad(vit, dxf[m.off * B:(m.off + m.n) * B], B, m.n, D, 1, 0, m.interp)
+    if defer_stems:
+        return dxf
+    encoder_backward_stems(vit, sv, dxf)
+    return None
+
+
+def encoder_backward_stems(vit, sv, dxf):
+    """Last part of the encoder backward: token assembly (instance-embedding gradient) and the conv stems of every expert modality."""
+    B, D = sv.B, vit.width
+    ie = getattr(vit, "instance_embedding", None)
+    dx0 = dxf
     branch = _branching(dx0.device, [m.domain for m in sv.mods])
     forks = []
     for i, m in enumerate(sv.mods):
         dt = dxf[m.off * B:(m.off + m.n) * B]
-        if pos_tr and not uniform:
-            _pos_grad(vit, dt, B, m.n, D, 1, 0, m.interp)           # shared table: stays on the calling stream
         if branch:
             forks.append(_fork(dx0.device, i))
             with torch.cuda.stream(forks[-1]):
@@ -1031,9 +1053,15 @@ def _backward_decoder(model, dsv, gscale):
     return denc
 
 
-def _backward_encoder(model, esv, denc):
-    encoder_backward(model.expert_encoder, esv, denc)
+def _backward_encoder(model, esv, denc, defer_stems: bool = False):
+    dxf = encoder_backward(model.expert_encoder, esv, denc, defer_stems)
     _side_join(_store(model).device)      # weight-gradient branch joins before the all-reduce / optimizer
+    return dxf
+
+
+def _backward_stems(model, esv, dxf):
+    encoder_backward_stems(model.expert_encoder, esv, dxf)
+    _side_join(_store(model).device)
 
 
 def _backward_train(model, esv, dsv, gscale):
@@ -1081,6 +1109,9 @@ def instance_map(entry) -> torch.Tensor:
     return inst if inst is not None else entry["label"].u8.long()
 
 
+DP_SEGMENTS = int(os.environ.get("PRISMER_DP_SEGMENTS", "3"))      # A/B switch: 2 = encoder backward and stems in one graph
+
+
 class GraphedTrainStep:
     """Forward + backward of one training step captured in ONE CUDA graph (static shapes): the ~1200 kernel launches of a
     step become a single ``cudaGraphLaunch``; dropout masks still change every replay (Philox key lives in device memory
@@ -1088,9 +1119,10 @@ class GraphedTrainStep:
     the host before every replay and copied into a static device buffer.  Gradients land in the flat fp32 buffer."""
 
     def __init__(self, model, experts, input_ids, attention_mask, labels, weights=None, warmup: int = 2, overlap: bool = False):
-        """``overlap=True`` captures TWO graphs (forward + decoder backward | encoder backward) so that a data-parallel caller
-        can all-reduce the decoder slice of the flat gradient buffer (``store.grad_t[:store.n_train_dec]``, 72 % of the bytes
-        for BASE freeze_vision) while the encoder backward runs: ``step(comm)``.
+        """``overlap=True`` captures THREE graphs (forward + decoder backward | encoder backward up to the stems | expert stems) so that
+        a data-parallel caller can all-reduce the decoder slice of the flat gradient buffer (``store.grad_t[:store.n_train_dec]``, 72 % of
+        the bytes for BASE freeze_vision) while the encoder backward runs and the ViT / resampler slice while the stems' backward runs;
+        only the stems' slice (``store.grad_t[store.n_train_late:]``, ~10 %) is reduced after the last kernel: ``step(comm)``.
         (Capturing the NCCL all-reduces INSIDE one graph was tried in round 2 and hung at replay on 2 GPUs with torch 2.11 / NCCL 2.28;
         the collectives therefore stay between the two graphs.)"""
         self.model = model
@@ -1129,8 +1161,13 @@ class GraphedTrainStep:
                 del dsv
             self.graph2 = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(self.graph2, pool=self.graph.pool()):
-                _backward_encoder(model, esv, denc)
-            self._keep = (esv, denc)                    # activations / boundary gradient shared by the two graphs
+                dxf = _backward_encoder(model, esv, denc, defer_stems=DP_SEGMENTS >= 3)
+            self.graph3 = None
+            if dxf is not None:
+                self.graph3 = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(self.graph3, pool=self.graph.pool()):
+                    _backward_stems(model, esv, dxf)
+            self._keep = (esv, denc, dxf)               # activations / boundary gradients shared by the graphs
         self.loss = loss
         st.publish_grads()
 
@@ -1176,8 +1213,14 @@ class GraphedTrainStep:
                         h1 = None
                     on_decoder_grads()
             self.graph2.replay()
-            h2 = comm(st.grad_t[st.n_train_dec:]) if comm is not None else None
-            for h in (h1, h2):
+            h3 = None
+            if self.graph3 is not None:                 # everything but the stems' slice is reduced under the stems' backward
+                h2 = comm(st.grad_t[st.n_train_dec:st.n_train_late]) if comm is not None and st.n_train_late > st.n_train_dec else None
+                self.graph3.replay()
+                h3 = comm(st.grad_t[st.n_train_late:]) if comm is not None and st.n_train > st.n_train_late else None
+            else:
+                h2 = comm(st.grad_t[st.n_train_dec:]) if comm is not None else None
+            for h in (h1, h2, h3):
                 if h is not None:
                     h.wait()
             if on_decoder_grads is not None:

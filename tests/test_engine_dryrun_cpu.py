@@ -209,8 +209,12 @@ def test_graphed_train_step_host_code(dry, fake_cuda, overlap, compact):
     handles = []
     comm = lambda t: (handles.append(t.numel()), type("H", (), {"wait": lambda self: None})())[1]
     loss = graphed(comm)
-    assert loss is graphed.loss and _FakeGraph.replays == (2 if overlap else 1)
-    assert handles == ([st.n_train_dec, st.grad_t.numel() - st.n_train_dec] if overlap else [st.grad_t.numel()])
+    assert loss is graphed.loss and _FakeGraph.replays == (3 if overlap else 1)     # fwd + decoder bwd | encoder bwd | expert stems
+    assert 0 < st.n_train_dec < st.n_train_late < st.n_train
+    late = [n for n, p in m.named_parameters() if p.requires_grad and engine._store(m)._offset[id(p)][1] >= st.n_train_late]
+    assert late and all("conv1." in n and "conv1.rgb" not in n or "instance_embedding" in n for n in late), late
+    assert handles == ([st.n_train_dec, st.n_train_late - st.n_train_dec, st.grad_t.numel() - st.n_train_late] if overlap
+                       else [st.grad_t.numel()])
     if overlap:                                                      # optimizer update of the decoder slice during the encoder backward
         n0 = dry.calls.get("prismer_adamw_step", 0)
         graphed(comm, on_decoder_grads=lambda: opt.step_range(0, st.n_train_dec, True, False))
