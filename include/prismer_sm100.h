@@ -180,7 +180,9 @@ int prismer_embed_fwd(const void* ids, const void* word, const void* pos, const 
                       int T, int H, int pad_id, int past_len, cudaStream_t stream);
 int prismer_embed_bwd(const void* de, const void* ids, const int* pos_ids, float* dword, float* dpos, float* dtype, int rows,
                       int H, int pad_id, cudaStream_t stream);
-/* logits fp32 [B*T, V] (ld); labels int64 [B,T] (unshifted, -100 = ignore); label smoothing; per-sample sums; mean. */
+/* logits fp32 [B*T, V] (ld); labels int64 [B,T] (unshifted, -100 = ignore); label smoothing; per-sample sums; mean.
+ * One pass over every row; 128-bit loads when ld % 4 == 0 and the buffer is 16-byte aligned (any ld otherwise).  The backward writes bf16
+ * dlogits [B*T, ldo] with columns [V, ldo) zeroed. */
 int prismer_ce_loss_fwd(const float* logits, long long ld, const void* labels, const float* weights, float* row_loss,
                         float* row_lse, float* sample_loss, float* mean_loss, int B, int T, int V, float smoothing,
                         cudaStream_t stream);
@@ -215,6 +217,8 @@ int prismer_patchify(const float* x, void* out, int B, int Cin, int R, int p, in
 int prismer_resample_bilinear(const float* x, void* out, int B, int C, int Hi, int Wi, int Ho, int Wo, cudaStream_t stream);
 int prismer_im2col_first(const void* in, int in_is_bf16, long long sb, long long sc, long long sy, long long sx, void* out,
                          int B, int Cin, int H, int W, int ksz, int stride, int Ho, int Wo, int Kpad, cudaStream_t stream);
+/* im2col of an NHWC bf16 activation (C % 8 == 0, C <= 3072; ksz 3 with padding 1, or 1); scale / shift (both or neither): the producer's
+ * BatchNorm affine + ReLU applied on load.  out [B*Ho*Wo, ksz*ksz*C]. */
 int prismer_im2col_nhwc(const void* in, const float* scale, const float* shift, void* out, int B, int H, int W, int C, int ksz,
                         int stride, int Ho, int Wo, cudaStream_t stream);
 /* BatchNorm2d (eps 1e-5, momentum 0.1): batch statistics in training (running stats updated in place) or running stats in
@@ -222,7 +226,9 @@ int prismer_im2col_nhwc(const void* in, const float* scale, const float* shift, 
 int prismer_bn_stats(const void* y, float* acc, long long M, int C, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, float* scale, float* shift, float* mean, float* rstd, float eps, float momentum,
                      int training, cudaStream_t stream);
-/* BatchNorm(train) + ReLU backward fused with the consumer conv's col2im: dAcol -> dy (grad wrt the raw conv output). */
+/* BatchNorm(train) + ReLU backward fused with the consumer conv's col2im: dAcol -> dy (grad wrt the raw conv output).
+ * (ksz, stride) describe the CONSUMER conv: (3, 2), (3, 1) (padding 1) or (1, 1); C % 8 == 0, C <= 3072; B*H*W < 2^31.
+ * red: fp32 [2, C] scratch (sum dn | sum dn*xhat); dgamma / dbeta (+=) may be NULL for a frozen BatchNorm. */
 int prismer_bn_relu_bwd(const void* dAcol, const void* y, const float* scale, const float* shift, const float* mean,
                         const float* rstd, const float* gamma, void* dn_scratch, void* dy, float* red, float* dgamma,
                         float* dbeta, int B, int H, int W, int C, int ksz, int stride, int Ho, int Wo, cudaStream_t stream);
