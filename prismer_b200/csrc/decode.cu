@@ -15,10 +15,11 @@
 #include "common.cuh"
 #include "prismer_sm100.h"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kRows = 32;        // rows per CTA (two m16 tiles)
-constexpr int kCols = 16;        // columns per CTA (two n8 tiles)
 constexpr int kKc = 1024;        // K chunk staged in shared memory
 constexpr int kPad = 8;
 
@@ -55,11 +56,14 @@ struct SkinnyParams {
 // Every global byte this CTA needs (its 16 x Kc weight slice and the 32 x Kc activation rows) is requested up front with cp.async --
 // ONE memory round trip per K chunk instead of a dependent load per k-step (the first version of this kernel was latency-bound:
 // 134 ms per 19-token decode).  The products then run from shared memory with ldmatrix + mma.sync; the 4 warps split the k-steps.
+// COLS = 16 (body layers: N <= 3072, one wave of CTAs) or 64 (tied LM head, N = 50265: with 16 columns the 3142 CTAs re-read the 48 KB of
+// x from L2 150 MB worth per launch -- more than the 77 MB of weights they stream).  The arithmetic per output element is the same.
+template <int COLS>
 __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * kCols, m0 = blockIdx.y * kRows;
-  const int mrows = min(kRows, p.M - m0), ncols = min(kCols, p.N - n0);
+  const int n0 = blockIdx.x * COLS, m0 = blockIdx.y * kRows;
+  const int mrows = min(kRows, p.M - m0), ncols = min(COLS, p.N - n0);
   const int kc_max = min(p.K, p.kc_len), ld = kc_max + kPad;
   bf16* sx = reinterpret_cast<bf16*>(smem_raw);
   bf16* sw = sx + kRows * ld;
@@ -74,11 +78,11 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
-  float acc[2][2][4];
+  float acc[2][COLS / 8][4];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
+    for (int b = 0; b < COLS / 8; ++b) acc[a][b][0] = acc[a][b][1] = acc[a][b][2] = acc[a][b][3] = 0.f;
 
   for (int kc = 0; kc < p.K; kc += p.kc_len) {
     const int kn = min(p.kc_len, p.K - kc);                     // multiple of 16 (checked on the host)
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
       const bool ok = r < mrows;
       cp_async16(sx + r * ld + c * 8, p.x + static_cast<long long>(ok ? m0 + r : m0) * p.ldx + kc + c * 8, ok);
     }
-    for (int i = threadIdx.x; i < kCols * vpr; i += 128) {
+    for (int i = threadIdx.x; i < COLS * vpr; i += 128) {
       const int r = i / vpr, c = i % vpr;
       const bool ok = r < ncols;
       cp_async16(sw + r * ld + c * 8, p.w + static_cast<long long>(ok ? n0 + r : n0) * p.ldw + kc + c * 8, ok);
@@ -101,12 +105,15 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
       uint32_t a0[4], a1[4], bw[4];
       ldsm_x4(a0, sx + (lane & 15) * ld + s * 16 + (lane >> 4) * 8);
       ldsm_x4(a1, sx + (16 + (lane & 15)) * ld + s * 16 + (lane >> 4) * 8);
-      // B operand ([n][k] tile, k contiguous): bw[0], bw[1] = n8 tile 0; bw[2], bw[3] = n8 tile 1
-      ldsm_x4(bw, sw + ((lane & 7) + (lane >> 4) * 8) * ld + s * 16 + ((lane >> 3) & 1) * 8);
-      mma16816(acc[0][0], a0, bw[0], bw[1]);
-      mma16816(acc[0][1], a0, bw[2], bw[3]);
-      mma16816(acc[1][0], a1, bw[0], bw[1]);
-      mma16816(acc[1][1], a1, bw[2], bw[3]);
+      // B operand ([n][k] tile, k contiguous): bw[0], bw[1] = n8 tile 0; bw[2], bw[3] = n8 tile 1 of every 16-column group
+#pragma unroll
+      for (int g = 0; g < COLS / 16; ++g) {
+        ldsm_x4(bw, sw + (g * 16 + (lane & 7) + (lane >> 4) * 8) * ld + s * 16 + ((lane >> 3) & 1) * 8);
+        mma16816(acc[0][2 * g], a0, bw[0], bw[1]);
+        mma16816(acc[0][2 * g + 1], a0, bw[2], bw[3]);
+        mma16816(acc[1][2 * g], a1, bw[0], bw[1]);
+        mma16816(acc[1][2 * g + 1], a1, bw[2], bw[3]);
+      }
     }
   }
   // cross-warp reduction of the split-K partials through shared memory: red[warp][row][col]
@@ -115,18 +122,18 @@ __global__ void __launch_bounds__(128) skinny_linear_kernel(SkinnyParams p) {
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+    for (int nt = 0; nt < COLS / 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int r = mt * 16 + (lane >> 2) + (e >> 1) * 8, c = nt * 8 + 2 * (lane & 3) + (e & 1);
-        red[(warp * kRows + r) * kCols + c] = acc[mt][nt][e];
+        red[(warp * kRows + r) * COLS + c] = acc[mt][nt][e];
       }
   __syncthreads();
-  for (int o = threadIdx.x; o < kRows * kCols; o += 128) {
-    const int r = o / kCols, c = o % kCols;
+  for (int o = threadIdx.x; o < kRows * COLS; o += 128) {
+    const int r = o / COLS, c = o % COLS;
     const int m = m0 + r, n = n0 + c;
     if (r >= mrows || n >= p.N) continue;
-    float v = red[o] + red[kRows * kCols + o] + red[2 * kRows * kCols + o] + red[3 * kRows * kCols + o];
+    float v = red[o] + red[kRows * COLS + o] + red[2 * kRows * COLS + o] + red[3 * kRows * COLS + o];
     if (p.bias) v += p.bias[n];
     v = act_fwd(p.act, v);
     if (p.residual) v += __bfloat162float(p.residual[static_cast<long long>(m) * p.ldr + n]);
@@ -253,23 +260,28 @@ extern "C" int prismer_skinny_linear(const void* x, long long ldx, const void* w
   p.x = reinterpret_cast<const bf16*>(x); p.ldx = ldx; p.w = reinterpret_cast<const bf16*>(w); p.ldw = ldw; p.bias = bias;
   p.residual = reinterpret_cast<const bf16*>(residual); p.ldr = ldr; p.out = out; p.ldo = ldo; p.out_fp32 = out_fp32;
   p.M = M; p.N = N; p.K = K; p.act = act;
+  // 64 columns per CTA for vocabulary-sized N (the tied LM head), 16 otherwise
+  static const bool wide_ok = [] { const char* e = getenv("PRISMER_SKINNY_WIDE"); return !(e && e[0] == '0'); }();
+  const int cols = (wide_ok && N >= 8192) ? 64 : 16;
   // K chunk per shared-memory round trip: the whole K (<= 1024) when the grid fits one wave -- a single memory round trip per CTA --,
-  // 256 when there are many more CTAs than SMs (LM head: 3142 CTAs): 25 KB of shared memory per CTA, 8 CTAs per SM hide each other's latency
-  const long long ctas = static_cast<long long>((N + kCols - 1) / kCols) * ((M + kRows - 1) / kRows);
+  // 256 when there are many more CTAs than SMs (LM head): several CTAs per SM hide each other's latency
+  const long long ctas = static_cast<long long>((N + cols - 1) / cols) * ((M + kRows - 1) / kRows);
   int kc = K < kKc ? K : kKc;
   if (ctas > 3 * 148 && kc > 256) kc = 256;
   p.kc_len = kc;
-  size_t smem = static_cast<size_t>(kRows + kCols) * (kc + kPad) * 2;
-  const size_t red = static_cast<size_t>(4) * kRows * kCols * 4;
+  size_t smem = static_cast<size_t>(kRows + cols) * (kc + kPad) * 2;
+  const size_t red = static_cast<size_t>(4) * kRows * cols * 4;
   if (smem < red) smem = red;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(skinny_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + kCols) * (kKc + kPad) * 2) != cudaSuccess)
+    if (cudaFuncSetAttribute(skinny_linear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + 16) * (kKc + kPad) * 2) != cudaSuccess ||
+        cudaFuncSetAttribute(skinny_linear_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kRows + 64) * (kKc + kPad) * 2) != cudaSuccess)
       return PRISMER_ERR_CUDA;
     configured = true;
   }
-  dim3 grid((N + kCols - 1) / kCols, (M + kRows - 1) / kRows);
-  pdl_launch(skinny_linear_kernel, grid, dim3(128), smem, stream, p);
+  dim3 grid((N + cols - 1) / cols, (M + kRows - 1) / kRows);
+  if (cols == 64) pdl_launch(skinny_linear_kernel<64>, grid, dim3(128), smem, stream, p);
+  else pdl_launch(skinny_linear_kernel<16>, grid, dim3(128), smem, stream, p);
   return LAUNCH_CHECK();
 }
 
