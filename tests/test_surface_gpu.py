@@ -88,14 +88,15 @@ def test_graphed_step_equals_eager_step():
     assert abs(float(l2) - float(loss)) < 1e-3 * abs(float(loss))
     # identical kernels on identical inputs; split-K / atomics only reorder fp32 additions
     assert err < 2e-3
-    # two-graph variant (decoder slice of the gradients finished early for the overlapped all-reduce): same gradients
+    # three-graph variant (decoder slice of the gradients finished first, the stems' slice last, for the overlapped all-reduces): same gradients
     g2 = engine.GraphedTrainStep(m, ex, ids, mask, labels, warmup=1, overlap=True)
     calls = []
     random.seed(1)
     g2(lambda t: (calls.append(t.numel()), type("H", (), {"wait": lambda self: None})())[1])
     torch.cuda.synchronize()
     assert rel_l2(st.grad_t, g_eager) < 2e-3
-    assert calls == [st.n_train_dec, st.grad_t.numel() - st.n_train_dec] and 0 < st.n_train_dec < st.grad_t.numel()
+    assert 0 < st.n_train_dec < st.n_train_late < st.grad_t.numel()
+    assert calls == [st.n_train_dec, st.n_train_late - st.n_train_dec, st.grad_t.numel() - st.n_train_late]
 
 
 def test_vqa_train_and_rank_ids_match_oracle():
