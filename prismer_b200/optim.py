@@ -50,10 +50,33 @@ class FusedAdamW:
         if last:
             st.mark_fresh()
 
+    def _layout(self):
+        """(name, offset, numel) of every trainable parameter in the flat buffers -- stored with the moments so that a checkpoint
+        does not depend on the buffer layout (which follows the backward's completion order and may change between versions)."""
+        st = self.store
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        return [(names[id(p)], st._offset[id(p)][1], p.numel()) for p in st.train_params]
+
     def state_dict(self):
-        return {"m": self.m, "v": self.v, "t": self.t, "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
+        return {"m": self.m, "v": self.v, "t": self.t, "layout": self._layout(),
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 
     def load_state_dict(self, sd):
-        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = int(sd["t"])
+        mine, theirs = self._layout(), sd.get("layout")
+        if theirs is None or [tuple(x) for x in theirs] == mine:
+            if sd["m"].numel() != self.m.numel():
+                raise ValueError(f"optimizer state holds {sd['m'].numel()} elements, this model's trainable buffer {self.m.numel()}")
+            self.m.copy_(sd["m"]); self.v.copy_(sd["v"])
+        else:                                                   # saved under another layout: move every parameter's slice by name
+            src = {n: (o, k) for n, o, k in theirs}
+            missing = [n for n, _, _ in mine if n not in src]
+            if missing:
+                raise KeyError(f"optimizer state has no moments for {len(missing)} trainable parameters, e.g. {missing[:3]}")
+            for n, o, k in mine:
+                so, sk = src[n]
+                if sk != k:
+                    raise ValueError(f"optimizer state of {n}: {sk} elements, expected {k}")
+                self.m[o:o + k].copy_(sd["m"][so:so + k]); self.v[o:o + k].copy_(sd["v"][so:so + k])
+        self.t = int(sd["t"])
         for g, saved in zip(self.param_groups, sd.get("param_groups", [])):     # lr (schedules), betas, eps, weight_decay
             g.update({k: v for k, v in saved.items() if k != "params"})

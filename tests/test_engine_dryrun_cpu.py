@@ -319,3 +319,31 @@ def test_accelerator_save_state_load_state_roundtrip(dry, tmp_path):
     assert torch.equal(opt2.m, opt.m) and torch.equal(opt2.v, opt.v) and opt2.t == 7 and opt2.param_groups[0]["lr"] == 1.25e-5
     assert int(engine._store(m2).seed.item()) == 4321
     assert random.random() == want_r and torch.equal(torch.rand(3), want_t)
+
+
+def test_optimizer_state_survives_a_layout_change(dry):
+    """The flat buffers follow the backward's completion order (decoder | ViT + resampler | stems); a checkpoint written under another
+    order is re-mapped parameter by parameter through the names stored with it, and a foreign one fails loudly."""
+    from prismer_b200.optim import FusedAdamW
+    m = _tiny(True)
+    opt = FusedAdamW(m, lr=1e-3)
+    opt.m.normal_(); opt.v.uniform_(); opt.t = 3
+    sd = opt.state_dict()
+    lay = sd["layout"]
+    assert [n for n, _, _ in lay] == [n for n, p in sorted(((n, p) for n, p in m.named_parameters() if p.requires_grad),
+                                                           key=lambda np_: engine._store(m)._offset[id(np_[1])][1])]
+    # the same moments laid out in reverse parameter order
+    rev, off = [], 0
+    m_rev, v_rev = torch.zeros_like(opt.m), torch.zeros_like(opt.v)
+    for n, o, k in reversed(lay):
+        m_rev[off:off + k] = opt.m[o:o + k]; v_rev[off:off + k] = opt.v[o:o + k]
+        rev.append((n, off, k)); off += (k + 7) // 8 * 8
+    opt2 = FusedAdamW(m, lr=1e-3)
+    opt2.load_state_dict({"m": m_rev, "v": v_rev, "t": 3, "layout": rev, "param_groups": sd["param_groups"]})
+    for n, o, k in lay:
+        assert torch.equal(opt2.m[o:o + k], opt.m[o:o + k]) and torch.equal(opt2.v[o:o + k], opt.v[o:o + k]), n
+    assert opt2.t == 3
+    with pytest.raises(KeyError):
+        opt2.load_state_dict({"m": m_rev, "v": v_rev, "t": 3, "layout": [("not.a.parameter", 0, 8)], "param_groups": []})
+    with pytest.raises(ValueError):
+        opt2.load_state_dict({"m": m_rev[:8], "v": v_rev[:8], "t": 3, "param_groups": []})
