@@ -1124,7 +1124,7 @@ class GraphedTrainStep:
         the bytes for BASE freeze_vision) while the encoder backward runs and the ViT / resampler slice while the stems' backward runs;
         only the stems' slice (``store.grad_t[store.n_train_late:]``, ~10 %) is reduced after the last kernel: ``step(comm)``.
         (Capturing the NCCL all-reduces INSIDE one graph was tried in round 2 and hung at replay on 2 GPUs with torch 2.11 / NCCL 2.28;
-        the collectives therefore stay between the two graphs.)"""
+        the collectives therefore stay between the graphs.)"""
         self.model = model
         self.overlap = overlap
         st = self.store = _store(model)
